@@ -1,0 +1,154 @@
+"""Independent numpy restatement of the reference (small cases only) used to cross-check oracle/vi_oracle.c.
+
+TEST INFRASTRUCTURE ONLY (same rules as oracle/__init__.py).  Written separately from the C oracle, directly from
+VectorIndex/IndexBuilder.cs:23-198 and DDL.sql:246-295: numpy float32 arrays evaluate each `+ - * /` as one IEEE
+binary32 operation per element, which is what the C# `float` code does; Python ints stand in for Int128.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _trunc_div(a: int, b: int) -> int:
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b > 0) else -q
+
+
+def _cmp_dotnet(a: np.float32, b: np.float32) -> int:
+    # float.CompareTo: NaN lowest, -0 == +0
+    if a < b:
+        return -1
+    if a > b:
+        return 1
+    if a == b:
+        return 0
+    if np.isnan(a):
+        return 0 if np.isnan(b) else -1
+    return 1
+
+
+def build_literal(ids, rows):
+    """Returns list of (rangeId, Dimension, Mid, Id) in the reference's emission order."""
+    rows = np.asarray(rows, np.float32)
+    ids = [int(i) for i in ids]
+    out = []
+    stack = [(0, list(range(len(ids))), True)]  # IndexBuilder.cs:33
+    while stack:
+        range_id, pts, mx = stack.pop()  # :37
+        if not pts:
+            continue  # :70-73
+        mean = rows[pts[0]].copy()  # :159-173
+        q = np.zeros_like(mean)
+        idn = ids[pts[0]]
+        count = 1
+        with np.errstate(all="ignore"):
+            for p in pts[1:]:  # :175-197
+                v = rows[p]
+                count += 1
+                c = np.float32(count)
+                pa = mean
+                a = pa + (v - pa) / c
+                q = q + (v - pa) * (v - a)
+                mean = a
+                idn += ids[p]
+        if count == 1:
+            out.append((range_id, -1, np.float32(0), idn))  # :81-82
+            continue
+        keys = q if mx else -q
+        index = 0
+        for i in range(1, len(keys)):  # MaxBy, strictly greater replaces (:77-79)
+            if _cmp_dotnet(keys[i], keys[index]) > 0:
+                index = i
+        mid = mean[index]
+        pivot = _trunc_div(idn, count)  # :87
+        out.append((range_id, index, mid, pivot))
+        if range_id > (2 ** 63 - 1 - 2) // 2:
+            raise OverflowError("checked(rangeId * 2 + 2)")  # :99,104
+        lo, hi = [], []
+        for p in pts:  # :111-124
+            value = rows[p, index]
+            if value > mid or (value == mid and ids[p] > pivot):
+                hi.append(p)
+            else:
+                lo.append(p)
+        stack.append((2 * range_id + 1, lo, not mx))  # :128
+        stack.append((2 * range_id + 2, hi, not mx))  # :129
+    return out
+
+
+def build_q30(ids, rows):
+    """The fast-mode specification: exact integer sums of xi = rint(x * 2^(30-E))."""
+    rows = np.asarray(rows, np.float32)
+    ids = [int(i) for i in ids]
+    finite = np.abs(rows[np.isfinite(rows)])
+    amax = np.float32(finite.max()) if finite.size else np.float32(0)
+    if np.isinf(np.abs(rows)).any():
+        e = 128
+    elif amax > 0:
+        _, e = np.frexp(amax)
+        e = int(e)
+    else:
+        e = 0
+    e = min(max(e, -96), 128)
+    k = np.float32(2.0) ** np.float32(30 - e)
+    with np.errstate(all="ignore"):
+        y = rows * k
+    y = np.where(np.isnan(y), np.float32(0), y)
+    xi = np.clip(np.rint(y.astype(np.float64)), -2 ** 31, 2 ** 31 - 1).astype(np.int64)
+    out = []
+    stack = [(0, list(range(len(ids))), True)]
+    while stack:
+        range_id, pts, mx = stack.pop()
+        if not pts:
+            continue
+        n = len(pts)
+        idn = sum(ids[p] for p in pts)
+        if n == 1:
+            out.append((range_id, -1, np.float32(0), idn))
+            continue
+        sub = xi[pts]
+        s1 = [int(v) for v in sub.sum(axis=0)]
+        s2 = [sum(int(v) * int(v) for v in sub[:, j]) for j in range(sub.shape[1])]
+        keys = [n * b - a * a for a, b in zip(s1, s2)]
+        index = 0
+        for i in range(1, len(keys)):
+            if (keys[i] > keys[index]) if mx else (keys[i] < keys[index]):
+                index = i
+        mid = np.float32((np.float64(s1[index]) / np.float64(n)) * np.float64(2.0) ** (e - 30))
+        pivot = _trunc_div(idn, n)
+        out.append((range_id, index, mid, pivot))
+        lo, hi = [], []
+        for p in pts:
+            value = rows[p, index]
+            if value > mid or (value == mid and ids[p] > pivot):
+                hi.append(p)
+            else:
+                lo.append(p)
+        stack.append((2 * range_id + 1, lo, not mx))
+        stack.append((2 * range_id + 2, hi, not mx))
+    return out
+
+
+def search(table: dict, query, proximity):
+    """dbo.Search over {rangeId: (Dimension, Mid, Id)} (DDL.sql:246-295). Returns ids in DFS order, low first."""
+    query = np.asarray(query, np.float32)
+    p = np.float32(proximity)
+    out = []
+    stack = [0]
+    while stack:
+        r = stack.pop()
+        row = table.get(r)
+        if row is None:
+            continue
+        dim, mid, rid = row
+        if dim < 0:
+            out.append(rid)
+            continue
+        lo = np.float32(query[dim] - p)
+        hi = np.float32(query[dim] + p)
+        mid = np.float32(mid)
+        if mid <= hi:
+            stack.append(2 * r + 2)
+        if mid >= lo:
+            stack.append(2 * r + 1)
+    return out

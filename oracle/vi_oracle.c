@@ -1,0 +1,361 @@
+/*
+ * vi_oracle.c -- CPU ORACLE for the split-tree vector index.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is a plain-C restatement of the reference's algorithm for the hot path.  It exists so the
+ * CUDA path can be checked against it.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` leg may load it.  The product (vector-database_b200/) never links, imports or calls it.
+ *
+ * PARITY UNPINNED: the reference cannot run in this image (no .NET SDK, no SQL Server) and its own tests
+ * hold no golden vector / known-answer test for IndexBuilder.Build or dbo.Search.
+ * The oracle is therefore anchored on the reference's *source text*, cited line by line below, plus
+ * hand-derivable known answers kept in tests/test_oracle_kat.py and an independent numpy restatement in
+ * oracle/np_oracle.py.
+ *
+ * Reference files followed (paths relative to /root/reference):
+ *   VectorIndex/IndexBuilder.cs:23-157   Build driver loop (DFS over ranges, explicit stack)
+ *   VectorIndex/IndexBuilder.cs:159-173  InitStats  (first point of a range)
+ *   VectorIndex/IndexBuilder.cs:175-197  UpdateStats (float32 Welford recurrence + Int128 id sum)
+ *   VectorIndex/IndexBuilder.cs:77-88    split choice (MaxBy, first index wins) and RangeValue fields
+ *   VectorIndex/IndexBuilder.cs:111-124  stable partition at Mid with the id tie-break
+ *   VectorIndex/Stats.cs:6-27            accumulator field types (float Mean, float Stdev2N, long Count, Int128 IdN)
+ *   VectorIndex/RangeValue.cs:6-22       output row (int Dimension, float Mid, long Id)
+ *   DDL.sql:246-295                      dbo.Search traversal (vector +- domain from RangeID 0)
+ *
+ * Build flags (oracle/Makefile): -O2 -ffp-contract=off -fno-fast-math -mfpmath=sse : every float operation is a
+ * single IEEE binary32 operation, exactly as RyuJIT x64 evaluates C# `float` arithmetic (no FMA contraction).
+ *
+ * Two build modes:
+ *   mode 0  "literal": the reference's arithmetic, bit for bit.
+ *   mode 1  "q30":     the B200 fast mode's *specification* (order-independent fixed-point integer sums),
+ *                      restated on the CPU so the GPU fast path can be checked bit-exactly against it.  It is
+ *                      not the reference's arithmetic; tests report its divergence from mode 0.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef __int128 i128;
+typedef unsigned __int128 u128;
+
+#define VIO_OK 0
+#define VIO_ERR_CAPACITY -1 /* output arrays too small */
+#define VIO_ERR_OVERFLOW -2 /* checked(rangeId*2+1/2) overflow, IndexBuilder.cs:99,104 */
+#define VIO_ERR_NOMEM -3
+#define VIO_ERR_ARG -4
+
+/* float.CompareTo as used by Comparer<float>.Default inside Enumerable.MaxBy (IndexBuilder.cs:77-79):
+ * NaN sorts below every number, NaN == NaN, -0 == +0. */
+static inline int cmp_float_dotnet(float a, float b)
+{
+  if (a < b) return -1;
+  if (a > b) return 1;
+  if (a == b) return 0;
+  if (isnan(a)) return isnan(b) ? 0 : -1;
+  return 1;
+}
+
+typedef struct
+{
+  int64_t range_id;
+  int64_t start;
+  int64_t count;
+  int max; /* IndexBuilder.cs:31 : (rangeId, store, max) */
+} work_item;
+
+typedef struct
+{
+  work_item* items;
+  int64_t size, cap;
+} work_stack;
+
+static int push(work_stack* s, work_item it)
+{
+  if (s->size == s->cap)
+  {
+    int64_t ncap = s->cap ? s->cap * 2 : 1024;
+    work_item* p = (work_item*)realloc(s->items, (size_t)ncap * sizeof(work_item));
+    if (!p) return 0;
+    s->items = p;
+    s->cap = ncap;
+  }
+  s->items[s->size++] = it;
+  return 1;
+}
+
+/* Quantisation exponent of the q30 mode: smallest E (clamped) with max|x| < 2^E, from frexp. */
+int vio_q30_exponent(const float* rows, int64_t n, int32_t d, int64_t ld)
+{
+  float amax = 0.0f;
+  for (int64_t r = 0; r < n; ++r)
+    for (int32_t i = 0; i < d; ++i)
+    {
+      float a = fabsf(rows[r * ld + i]);
+      if (a > amax) amax = a; /* NaN never wins: comparisons with NaN are false */
+    }
+  int e = 0;
+  if (amax > 0.0f && !isinf(amax)) (void)frexpf(amax, &e);
+  else if (isinf(amax)) e = 128;
+  if (e < -96) e = -96;
+  if (e > 128) e = 128;
+  return e;
+}
+
+static inline int32_t q30_quantise(float x, float k)
+{
+  /* GPU: __float2int_rn(x * k) : round-to-nearest-even, NaN -> 0, saturating. */
+  float y = x * k;
+  if (isnan(y)) return 0;
+  if (y >= 2147483648.0f) return INT32_MAX;
+  if (y <= -2147483648.0f) return INT32_MIN;
+  return (int32_t)lrintf(y);
+}
+
+/*
+ * Build the range table.
+ *   ids[n], rows[n*ld] (row r at rows + r*ld, d used floats), mode 0 literal / 1 q30.
+ * Output rows are written in the reference's emission order (DFS, high child popped first:
+ * IndexBuilder.cs:128-129 pushes low then high onto a Stack).  Returns VIO_OK and *out_count.
+ */
+int vio_build(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float* rows, int mode,
+              int64_t cap, int64_t* out_range_id, int32_t* out_dim, float* out_mid, int64_t* out_id,
+              int64_t* out_count)
+{
+  if (n < 0 || d <= 0 || ld < d || (mode != 0 && mode != 1)) return VIO_ERR_ARG;
+  *out_count = 0;
+  if (n == 0) return VIO_OK; /* IndexBuilder.cs:70-73 : empty root emits nothing */
+
+  int rc = VIO_OK;
+  int64_t* perm = (int64_t*)malloc((size_t)n * sizeof(int64_t));
+  int64_t* tmp = (int64_t*)malloc((size_t)n * sizeof(int64_t));
+  float* mean = (float*)malloc((size_t)d * sizeof(float));
+  float* q = (float*)malloc((size_t)d * sizeof(float));
+  int64_t* s1 = (int64_t*)malloc((size_t)d * sizeof(int64_t));
+  u128* s2 = (u128*)malloc((size_t)d * sizeof(u128));
+  work_stack st = {0, 0, 0};
+  if (!perm || !tmp || !mean || !q || !s1 || !s2) { rc = VIO_ERR_NOMEM; goto done; }
+  for (int64_t i = 0; i < n; ++i) perm[i] = i;
+
+  int qe = 0;
+  float qk = 1.0f;
+  double qinv = 1.0;
+  if (mode == 1)
+  {
+    qe = vio_q30_exponent(rows, n, d, ld);
+    qk = ldexpf(1.0f, 30 - qe);
+    qinv = ldexp(1.0, qe - 30);
+  }
+
+  work_item root = {0, 0, n, 1}; /* IndexBuilder.cs:33 */
+  if (!push(&st, root)) { rc = VIO_ERR_NOMEM; goto done; }
+
+  int64_t emitted = 0;
+  while (st.size > 0)
+  {
+    work_item it = st.items[--st.size]; /* IndexBuilder.cs:37 */
+    const int64_t* p = perm + it.start;
+    int64_t count = it.count;
+    if (count == 0) continue; /* IndexBuilder.cs:70-73 */
+
+    i128 idn = 0;
+    int32_t index = 0;
+    float mid = 0.0f;
+
+    if (mode == 0)
+    {
+      /* IndexBuilder.cs:159-173 InitStats */
+      const float* v0 = rows + p[0] * ld;
+      for (int32_t i = 0; i < d; ++i) { mean[i] = v0[i]; q[i] = 0.0f; }
+      idn = (i128)ids[p[0]];
+      /* IndexBuilder.cs:175-197 UpdateStats, binary32, one divide per (point, dim) */
+      for (int64_t j = 1; j < count; ++j)
+      {
+        const float* v = rows + p[j] * ld;
+        float c = (float)(j + 1); /* long -> float conversion of Count+1, IndexBuilder.cs:185-186 */
+        for (int32_t i = 0; i < d; ++i)
+        {
+          float value = v[i];
+          float pa = mean[i];
+          float pq = q[i];
+          float a = pa + (value - pa) / c;
+          float qq = pq + (value - pa) * (value - a);
+          mean[i] = a;
+          q[i] = qq;
+        }
+        idn += (i128)ids[p[j]];
+      }
+      /* IndexBuilder.cs:77-79 MaxBy(max ? Stdev2N : -Stdev2N): strictly-greater replacement */
+      float best = it.max ? q[0] : -q[0];
+      for (int32_t i = 1; i < d; ++i)
+      {
+        float key = it.max ? q[i] : -q[i];
+        if (cmp_float_dotnet(key, best) > 0) { best = key; index = i; }
+      }
+      mid = mean[index];
+    }
+    else
+    {
+      /* q30 specification (DESIGN.md "fast mode"): exact integer sums of xi = rint(x * 2^(30-E)). */
+      for (int32_t i = 0; i < d; ++i) { s1[i] = 0; s2[i] = 0; }
+      for (int64_t j = 0; j < count; ++j)
+      {
+        const float* v = rows + p[j] * ld;
+        for (int32_t i = 0; i < d; ++i)
+        {
+          int64_t xi = q30_quantise(v[i], qk);
+          s1[i] += xi;
+          s2[i] += (u128)(uint64_t)(xi * xi);
+        }
+        idn += (i128)ids[p[j]];
+      }
+      /* key K = n*S2 - S1^2 (exact, >= 0); even depth argmax, odd depth argmin, lowest index wins ties */
+      u128 bestk = 0;
+      for (int32_t i = 0; i < d; ++i)
+      {
+        i128 a = (i128)s1[i];
+        u128 k = (u128)(uint64_t)count * s2[i] - (u128)(a * a);
+        if (i == 0 || (it.max ? (k > bestk) : (k < bestk))) { bestk = k; index = i; }
+      }
+      mid = (float)(((double)s1[index] / (double)count) * qinv);
+    }
+
+    if (emitted >= cap) { rc = VIO_ERR_CAPACITY; goto done; }
+    out_range_id[emitted] = it.range_id;
+    if (count == 1)
+    {
+      /* IndexBuilder.cs:81-82 : leaf, Mid keeps its default 0 */
+      out_dim[emitted] = -1;
+      out_mid[emitted] = 0.0f;
+      out_id[emitted] = (int64_t)idn;
+      ++emitted;
+      continue; /* IndexBuilder.cs:94-97 */
+    }
+    int64_t pivot = (int64_t)(idn / (i128)count); /* IndexBuilder.cs:87, truncation toward zero */
+    out_dim[emitted] = index;
+    out_mid[emitted] = mid;
+    out_id[emitted] = pivot;
+    ++emitted;
+
+    /* IndexBuilder.cs:99,104 checked arithmetic */
+    if (it.range_id > (INT64_MAX - 2) / 2) { rc = VIO_ERR_OVERFLOW; goto done; }
+
+    /* IndexBuilder.cs:111-124 stable partition */
+    int64_t nlo = 0, nhi = 0;
+    int64_t* lo = perm + it.start;
+    int64_t* hi = tmp + it.start;
+    for (int64_t j = 0; j < count; ++j)
+    {
+      int64_t r = p[j];
+      float value = rows[r * ld + index];
+      int64_t id = ids[r];
+      if (value > mid || (value == mid && id > pivot)) hi[nhi++] = r;
+      else lo[nlo++] = r; /* in place: nlo <= j */
+    }
+    memcpy(perm + it.start + nlo, hi, (size_t)nhi * sizeof(int64_t));
+
+    work_item wlo = {it.range_id * 2 + 1, it.start, nlo, !it.max};
+    work_item whi = {it.range_id * 2 + 2, it.start + nlo, nhi, !it.max};
+    if (!push(&st, wlo) || !push(&st, whi)) { rc = VIO_ERR_NOMEM; goto done; } /* IndexBuilder.cs:128-129 */
+  }
+  *out_count = emitted;
+
+done:
+  free(perm); free(tmp); free(mean); free(q); free(s1); free(s2); free(st.items);
+  return rc;
+}
+
+/* ---- dbo.Search over IndexBuilder rows (DDL.sql:246-295) ------------------------
+ * Table is given sorted by range_id (ascending) so that a row is found by binary search, mirroring the
+ * clustered-index seek on TextIndex.RangeID.  A child row may be absent (empty range => no row).
+ * Leaf <=> Dimension == -1, its TextID is Id; internal rows have TextID = null (DDL.sql:195-197).
+ */
+static int64_t find_row(const int64_t* range_id, int64_t nrows, int64_t key)
+{
+  int64_t lo = 0, hi = nrows - 1;
+  while (lo <= hi)
+  {
+    int64_t m = lo + ((hi - lo) >> 1);
+    if (range_id[m] == key) return m;
+    if (range_id[m] < key) lo = m + 1; else hi = m - 1;
+  }
+  return -1;
+}
+
+/* One query. Writes up to cap ids (in DFS order, low branch first) and returns the total found in *out_n,
+ * and the number of rows visited in *out_visits. */
+int vio_search(int64_t nrows, const int64_t* range_id, const int32_t* dim, const float* mid,
+               const int64_t* id, int32_t d, const float* query, float proximity, int64_t cap,
+               int64_t* out_ids, int64_t* out_n, int64_t* out_visits)
+{
+  *out_n = 0;
+  if (out_visits) *out_visits = 0;
+  if (nrows == 0) return VIO_OK;
+  work_stack st = {0, 0, 0};
+  work_item root = {0, 0, 0, 0};
+  if (!push(&st, root)) return VIO_ERR_NOMEM;
+  int64_t found = 0, visits = 0;
+  while (st.size > 0)
+  {
+    int64_t r = st.items[--st.size].range_id;
+    int64_t row = find_row(range_id, nrows, r);
+    if (row < 0) continue; /* join finds no I row */
+    ++visits;
+    int32_t k = dim[row];
+    if (k < 0)
+    {
+      if (found < cap) out_ids[found] = id[row];
+      ++found;
+      continue;
+    }
+    if (k >= d) { free(st.items); return VIO_ERR_ARG; }
+    if (r > (INT64_MAX - 2) / 2) continue;
+    float lo = query[k] - proximity; /* DDL.sql:249-250, SQL `real` arithmetic */
+    float hi = query[k] + proximity;
+    work_item c = {0, 0, 0, 0};
+    /* push high first so that low is visited first */
+    if (mid[row] <= hi) { c.range_id = 2 * r + 2; if (!push(&st, c)) { free(st.items); return VIO_ERR_NOMEM; } } /* DDL.sql:280-293 */
+    if (mid[row] >= lo) { c.range_id = 2 * r + 1; if (!push(&st, c)) { free(st.items); return VIO_ERR_NOMEM; } } /* DDL.sql:265-278 */
+  }
+  free(st.items);
+  *out_n = found;
+  if (out_visits) *out_visits = visits;
+  return VIO_OK;
+}
+
+/* Batched form: CSR result. offsets[nq+1]; ids filled up to cap; *total = sum of counts. */
+int vio_search_batch(int64_t nrows, const int64_t* range_id, const int32_t* dim, const float* mid,
+                     const int64_t* id, int32_t d, int64_t nq, const float* queries, int64_t ldq,
+                     float proximity, int64_t cap, int64_t* offsets, int64_t* out_ids, int64_t* total,
+                     int64_t* total_visits)
+{
+  int64_t pos = 0, visits = 0;
+  offsets[0] = 0;
+  for (int64_t i = 0; i < nq; ++i)
+  {
+    int64_t n = 0, v = 0;
+    int64_t room = cap > pos ? cap - pos : 0;
+    int rc = vio_search(nrows, range_id, dim, mid, id, d, queries + i * ldq, proximity, room,
+                        out_ids ? out_ids + (pos < cap ? pos : cap) : 0, &n, &v);
+    if (rc != VIO_OK) return rc;
+    pos += n;
+    visits += v;
+    offsets[i + 1] = pos;
+  }
+  *total = pos;
+  if (total_visits) *total_visits = visits;
+  return VIO_OK;
+}
+
+/* Verification contract of Find(vector, distance, predicate) (MemoryVectorIndex.cs:237-245): the index
+ * returns candidates, the predicate decides.  Euclidean distance as in the reference's test helper
+ * (MemoryVectorIndexTests.cs:209-217): float32 accumulation in index order, then sqrt. */
+float vio_distance_l2(const float* a, const float* b, int32_t d)
+{
+  float s = 0.0f;
+  for (int32_t i = 0; i < d; ++i)
+  {
+    float t = a[i] - b[i];
+    s = s + t * t;
+  }
+  return sqrtf(s);
+}

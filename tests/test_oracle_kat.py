@@ -1,0 +1,197 @@
+"""Known answers for the oracle, hand-derived from IndexBuilder.cs / DDL.sql (SURVEY.md section 8c list),
+plus C-oracle vs independent numpy restatement cross-checks.  CPU only."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import np_oracle
+from vectorindex import synthetic as datasets
+
+
+def _tbl(ids, rows, mode=oracle.MODE_LITERAL):
+    return oracle.build(np.asarray(ids, np.int64), np.asarray(rows, np.float32), mode)
+
+
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+def test_empty(mode):
+    t = _tbl(np.zeros(0, np.int64), np.zeros((0, 4), np.float32), mode)
+    assert len(t) == 0  # IndexBuilder.cs:70-73
+
+
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+def test_single_point(mode):
+    t = _tbl([42], [[0.5, -0.25, 3.0]], mode)
+    assert t.as_dict() == {0: (-1, 0.0, 42)}  # IndexBuilder.cs:81-82
+
+
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+def test_two_points_one_dim_differs(mode):
+    # even depth => max variance => dim 1; mean 0.5; ids 7, 9 -> pivot trunc(16/2) = 8
+    t = _tbl([7, 9], [[1.0, 1.0, 1.0], [1.0, 0.0, 1.0]], mode).as_dict()
+    assert t[0] == (1, 0.5, 8)
+    assert t[1] == (-1, 0.0, 9)  # value 0.0 <= Mid -> low -> 2r+1
+    assert t[2] == (-1, 0.0, 7)  # value 1.0 > Mid -> high -> 2r+2
+    assert len(t) == 3
+
+
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+def test_identical_vectors_split_by_id(mode):
+    # IndexBuilder.cs:115 tie-break: value == Mid and id > Id -> high.  Id = trunc(13 / 2) = 6
+    t = _tbl([3, 10], [[0.25, 0.25], [0.25, 0.25]], mode).as_dict()
+    assert t[0] == (0, 0.25, 6)
+    assert t[1] == (-1, 0.0, 3)
+    assert t[2] == (-1, 0.0, 10)
+
+
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+def test_negative_ids_truncate_toward_zero(mode):
+    # Int128 division truncates toward zero (IndexBuilder.cs:87): (-3 + -6) / 2 = -4 (floor would give -5)
+    t = _tbl([-3, -6], [[0.5], [0.5]], mode).as_dict()
+    assert t[0] == (0, 0.5, -4)
+    assert t[1] == (-1, 0.0, -6)
+    assert t[2] == (-1, 0.0, -3)
+
+
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+def test_inseparable_points_overflow_at_depth_62(mode):
+    # ids {-4,-5}: pivot trunc(-9/2) = -4; neither id is > -4, both go low forever (a floor division would
+    # have separated them).  The reference dies with OverflowException from checked(rangeId*2+1)
+    # (IndexBuilder.cs:99); the oracle reports the same condition.
+    with pytest.raises(OverflowError):
+        _tbl([-4, -5], [[0.5], [0.5]], mode)
+
+
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+def test_min_variance_on_odd_depth(mode):
+    # 4 points, dim0 spread wide, dim1 constant, dim2 small spread.
+    rows = np.array([[-1.0, 0.5, 0.01], [-0.9, 0.5, -0.01], [0.9, 0.5, 0.02], [1.0, 0.5, -0.02]], np.float32)
+    t = _tbl([0, 1, 2, 3], rows, mode).as_dict()
+    assert t[0][0] == 0  # depth 0: max variance -> dim 0
+    # depth 1 (odd): min variance -> the constant dimension 1, Mid = 0.5, split purely by id
+    assert t[1][0] == 1 and t[1][1] == 0.5 and t[1][2] == 0  # ids {0,1} -> trunc(1/2) = 0
+    assert t[2][0] == 1 and t[2][1] == 0.5 and t[2][2] == 2  # ids {2,3} -> trunc(5/2) = 2
+    assert t[3] == (-1, 0.0, 0) and t[4] == (-1, 0.0, 1)
+    assert t[5] == (-1, 0.0, 2) and t[6] == (-1, 0.0, 3)
+
+
+def test_one_hot_sentinel_literal_vs_q30():
+    # Program.cs:54-66 crafted set.  All dimensions tie mathematically; literal float32 Welford breaks the tie
+    # by rounding noise and picks dimension 3 (hard part 1); exact integer sums pick dimension 0.
+    ids, rows = datasets.one_hot(1536)
+    lit = _tbl(ids, rows, oracle.MODE_LITERAL)
+    q30 = _tbl(ids, rows, oracle.MODE_Q30)
+    assert lit.dimension[0] == 3
+    assert q30.dimension[0] == 0
+    for t in (lit, q30):
+        assert (t.dimension == -1).sum() == 1536
+        assert sorted(t.id[t.dimension == -1].tolist()) == list(range(1536))
+
+
+def _check_invariants(t, ids):
+    d = t.as_dict()
+    leaves = t.dimension == -1
+    assert leaves.sum() == len(ids)
+    assert sorted(t.id[leaves].tolist()) == sorted(ids.tolist())
+    assert np.all(t.mid[leaves] == 0)
+    for r in d:
+        if r != 0:
+            assert (r - 1) // 2 in d and d[(r - 1) // 2][0] >= 0  # parent exists and is internal
+    assert len(t) == 2 * len(ids) - 1  # no empty child for distinct-id, finite data
+
+
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+def test_structural_invariants(mode):
+    ids, rows = datasets.uniform(3000, 24, seed=5)
+    ids = ids * 3 + 11
+    _check_invariants(_tbl(ids, rows, mode), ids)
+
+
+def test_emission_order_is_reference_dfs():
+    # IndexBuilder.cs:128-129 pushes low then high: high subtree is yielded first.
+    ids, rows = datasets.uniform(8, 3, seed=3)
+    t = _tbl(ids, rows)
+    order = t.emission_order.tolist()
+    assert order[0] == 0 and order[1] == 2
+
+
+@pytest.mark.parametrize("n,d,seed", [(1, 5, 0), (2, 5, 1), (17, 3, 2), (257, 16, 3), (600, 96, 4)])
+def test_c_oracle_matches_numpy_restatement_literal(n, d, seed):
+    ids, rows = datasets.uniform(n, d, seed)
+    ids = (ids * 7 + 5) % 1009  # non-monotone distinct ids
+    t = _tbl(ids, rows)
+    ref = np_oracle.build_literal(ids, rows)
+    assert [int(r) for r in t.emission_order] == [r[0] for r in ref]
+    d_ref = {r[0]: (r[1], float(r[2]), r[3]) for r in ref}
+    got = t.as_dict()
+    assert got.keys() == d_ref.keys()
+    for k in got:
+        assert got[k][0] == d_ref[k][0] and got[k][2] == d_ref[k][2]
+        assert np.float32(got[k][1]).tobytes() == np.float32(d_ref[k][1]).tobytes()
+
+
+@pytest.mark.parametrize("n,d,seed,scale", [(2, 5, 1, 1.0), (33, 3, 2, 1000.0), (300, 16, 3, 1e-3), (400, 96, 4, 1.0)])
+def test_c_oracle_matches_numpy_restatement_q30(n, d, seed, scale):
+    ids, rows = datasets.uniform(n, d, seed)
+    rows = (rows * np.float32(scale)).astype(np.float32)
+    t = _tbl(ids, rows, oracle.MODE_Q30)
+    ref = np_oracle.build_q30(ids, rows)
+    d_ref = {r[0]: (r[1], float(r[2]), r[3]) for r in ref}
+    got = t.as_dict()
+    assert got.keys() == d_ref.keys()
+    for k in got:
+        assert got[k][0] == d_ref[k][0] and got[k][2] == d_ref[k][2]
+        assert np.float32(got[k][1]).tobytes() == np.float32(d_ref[k][1]).tobytes()
+
+
+def test_duplicates_and_constant_columns():
+    # duplicated vectors with distinct ids must separate through the id tie-break
+    rng = np.random.default_rng(9)
+    base = rng.random((50, 6), dtype=np.float32)
+    rows = np.concatenate([base, base, base], 0)
+    rows[:, 2] = 0.125
+    ids = np.arange(150, dtype=np.int64)[::-1].copy()
+    for mode in (oracle.MODE_LITERAL, oracle.MODE_Q30):
+        _check_invariants(_tbl(ids, rows, mode), ids)
+
+
+def test_search_point_lookup_and_superset():
+    ids, rows = datasets.uniform(2000, 8, seed=6)
+    t = _tbl(ids, rows)
+    # p = 0 with q = dataset point returns that point's id
+    offs, out, visits = oracle.search(t, rows[:64], 0.0)
+    for i in range(64):
+        assert ids[i] in out[offs[i]:offs[i + 1]]
+    # result is a superset of the L-infinity box
+    p = np.float32(0.2)
+    q = rows[100:110] + np.float32(0.01)
+    offs, out, _ = oracle.search(t, q, float(p))
+    for i in range(q.shape[0]):
+        box = ids[np.all(np.abs(rows - q[i]) <= p, axis=1)]
+        got = set(out[offs[i]:offs[i + 1]].tolist())
+        assert set(box.tolist()) <= got
+    # C search == numpy restatement search (same DFS order)
+    td = t.as_dict()
+    for i in range(q.shape[0]):
+        assert out[offs[i]:offs[i + 1]].tolist() == np_oracle.search(td, q[i], p)
+
+
+def test_search_missing_child_rows():
+    # a table where a child row is absent (empty range => no row): traversal must tolerate it
+    t = oracle.RangeTable(np.array([0, 2], np.int64), np.array([0, -1], np.int32),
+                          np.array([0.5, 0.0], np.float32), np.array([1, 77], np.int64))
+    offs, out, visits = oracle.search(t, np.array([[0.5]], np.float32), 1.0)
+    assert out.tolist() == [77] and visits == 2
+
+
+def test_grid_search_equals_bruteforce_after_verify():
+    # property reused from MemoryVectorIndexTests.cs:161-204: candidates filtered by the Euclidean
+    # predicate == brute force set
+    ids, rows = datasets.grid2d(30)
+    t = _tbl(ids, rows)
+    q = np.array([[0.1, -0.3]], np.float32)
+    dist = 0.25
+    offs, out, _ = oracle.search(t, q, dist)
+    cand = out[offs[0]:offs[1]]
+    got = sorted(int(i) for i in cand if oracle.distance_l2(rows[i], q[0]) <= np.float32(dist))
+    want = sorted(int(i) for i in ids if oracle.distance_l2(rows[i], q[0]) <= np.float32(dist))
+    assert got == want and len(want) > 0
