@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- index build vectors/s (+ search queries/s) on the BASELINE.json workload.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # CPU arm: the literal oracle on the host cores
+
+A "step" is one full build of the split-tree index (IndexBuilder.Build, VectorIndex/IndexBuilder.cs:23-157) over one
+synthetic batch: N0 x 96 float32 rows, N(0,1) then L2-normalised (deep-image-96-angular shape), ids 0..N0-1.
+`value`  = vectors/s with the points already resident in HBM (vi_build only, CUDA events on the library's stream).
+`e2e`    = vectors/s through the C ABI with HOST buffers: vi_points_reserve + vi_points_add (H2D) + vi_build +
+           vi_ranges_copy (D2H of the range table) inside the timed region.
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "vector-database_b200"))
+
+import numpy as np  # noqa: E402
+
+DIMS = 96
+SEED = 2
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(levels, dims):
+    """B_l = A_l*(4*D + 28) + R_l*40 per level; statistics kernel alone: A_l*(4*D + 8 + 4)."""
+    whole = sum(l.points * (4 * dims + 28) + l.ranges * 40 for l in levels)
+    stats = sum(l.points * (4 * dims + 12) for l in levels)
+    return whole, stats
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                       "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                      text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_device(n, dims, seed, device):
+    """unit-normalised Gaussian rows generated on the GPU (torch is plumbing: device memory + RNG)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rows = torch.empty((n, dims), dtype=torch.float32, device=device)
+    chunk = 1 << 20
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        x = torch.randn((e - s, dims), generator=g, device=device, dtype=torch.float32)
+        rows[s:e] = x / x.norm(dim=1, keepdim=True)
+    ids = torch.arange(n, dtype=torch.int64, device=device)
+    return ids, rows
+
+
+def gen_queries(rows_d, nq, seed):
+    """half dataset rows, half fresh samples of the same distribution."""
+    import torch
+    g = torch.Generator(device=rows_d.device)
+    g.manual_seed(seed)
+    n = rows_d.shape[0]
+    pick = torch.randint(0, n, (nq // 2,), generator=g, device=rows_d.device)
+    a = rows_d[pick]
+    x = torch.randn((nq - nq // 2, rows_d.shape[1]), generator=g, device=rows_d.device, dtype=torch.float32)
+    b = x / x.norm(dim=1, keepdim=True)
+    return torch.cat([a, b], 0).contiguous()
+
+
+def cpu_baseline(rows_h, ids_h, sample_rows, threads=1):
+    """The literal oracle (port of IndexBuilder.cs) timed on the host: bounded sample of the same workload."""
+    import oracle
+    m = min(sample_rows, rows_h.shape[0])
+    t0 = time.perf_counter()
+    tbl = oracle.build(ids_h[:m], rows_h[:m], oracle.MODE_LITERAL)
+    dt = time.perf_counter() - t0
+    return {"value": m / dt, "unit": "vectors/s", "cores": threads, "kind": "port",
+            "sample": f"first {m} rows of the workload, one full literal build (oracle/vi_oracle.c, "
+                      f"-O2 -ffp-contract=off), {dt:.2f} s, {len(tbl)} ranges",
+            "host_cores_available": os.cpu_count()}, tbl
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (the oracle port; the C# original cannot run here: no .NET)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from vectorindex import synthetic as ds
+    import oracle
+    n = args.ref_rows
+    ids, rows = ds.unit_gaussian(n, DIMS, seed=SEED)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        tbl = oracle.build(ids, rows, oracle.MODE_LITERAL)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+        log(f"[reference] step {i}: {dt:.2f} s, {len(tbl)} ranges")
+    ms = 1000.0 * sum(times) / len(times)
+    v = n / (ms / 1000.0)
+    line = {"impl": "reference", "metric": "index_build_vectors_per_sec", "value": v, "unit": "vectors/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"deep-image-96-shaped synthetic {args.rows}x96 index build (IndexBuilder.Build)",
+                       "sample_rows": n, "mode": "literal float32 Welford (IndexBuilder.cs:175-197)"},
+            "cpu_baseline": {"value": v, "unit": "vectors/s", "cores": 1, "kind": "port",
+                             "sample": f"each step = one full literal build of a {n}-row sample of the workload "
+                                       f"(numpy seed {SEED}); the reference algorithm is strictly sequential",
+                             "host_cores_available": os.cpu_count()},
+            "e2e": {"value": v, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--ref-rows", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
+    ap.add_argument("--queries", type=int, default=1_000_000)
+    ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-exact", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        log("note: timing rules ask for >= 3 warm-up steps")
+
+    import torch
+    import vectorindex as vi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 or args.gpus > 1:
+        if rank == 0:
+            print(json.dumps({"error": "multi-GPU sharded build is not implemented yet in this revision", "n_gpus": args.gpus}))
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n = args.rows
+
+    t0 = time.perf_counter()
+    ids_d, rows_d = gen_device(n, DIMS, SEED, dev)
+    torch.cuda.synchronize()
+    log(f"generated {n}x{DIMS} rows on device in {time.perf_counter() - t0:.2f} s")
+
+    ctx = vi.Context(local)
+    ctx.reserve(n, DIMS)
+    ctx.add_device(ids_d.data_ptr(), rows_d.data_ptr(), n, DIMS)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def timed_builds(mode, warmup, steps):
+        for _ in range(warmup):
+            ctx.build(mode)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        evs = []
+        infos = []
+        for _ in range(steps):
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            infos.append(ctx.build(mode))
+            b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        ms = [a.elapsed_time(b) for a, b in evs]
+        return ms, infos, clocks
+
+    # ---- value: fast mode, device-resident ----------------------------------------------------------------------
+    ms, infos, clocks = timed_builds(vi.MODE_FAST, args.warmup, args.steps)
+    ms_per_step = sum(ms) / len(ms)
+    info = infos[-1]
+    levels = ctx.levels()
+    whole_b, stats_b = algorithmic_bytes(levels, DIMS)
+    stats_ms = sum(l.stats_ms for l in levels)
+    part_ms = sum(l.partition_ms for l in levels)
+    peak, peak_src = peaks()
+    n_stats_launch = sum(1 for l in levels if l.points > 0)
+    roofline = {"bound": "hbm", "kernel": "k_stats_big_q30 + k_stats_small_q30 (statistics pass, one per tree level)",
+                "achieved": stats_b / (stats_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": stats_b / (stats_ms / 1e3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": stats_b / max(n_stats_launch, 1),
+                "avg_launch_ms": stats_ms / max(n_stats_launch, 1),
+                "whole_build": {"algorithmic_bytes": whole_b, "achieved": whole_b / (ms_per_step / 1e3) / 1e9,
+                                "frac": whole_b / (ms_per_step / 1e3) / 1e9 / peak, "stats_ms": stats_ms,
+                                "partition_ms": part_ms},
+                "per_level": [{"level": l.level, "ranges": l.ranges, "points": l.points,
+                               "stats_ms": round(l.stats_ms, 4), "partition_ms": round(l.partition_ms, 4),
+                               "stats_gbs": (l.points * (4 * DIMS + 12) / (l.stats_ms / 1e3) / 1e9) if l.stats_ms > 0 else None}
+                              for l in levels]}
+    log(f"fast build: {ms_per_step:.2f} ms/step ({[round(x, 2) for x in ms]}), {info.ranges} ranges, {info.levels} levels, "
+        f"{info.kernel_launches} launches; stats {stats_ms:.2f} ms partition {part_ms:.2f} ms")
+
+    result = {"metric": "index_build_vectors_per_sec", "value": n / (ms_per_step / 1e3), "unit": "vectors/s",
+              "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i64 (q30 fixed-point sums of f32 rows)",
+              "data": "synthetic",
+              "config": {"workload": f"configs[1]: deep-image-96-angular-shaped synthetic {n}x{DIMS} index build on 1 B200",
+                         "mode": "fast (q30 order-independent integer statistics)", "rows": n, "dims": DIMS,
+                         "l2": "inputs (3.84 GB of rows per level) are larger than the 126 MB L2; no flush needed",
+                         "ranges": int(info.ranges), "levels": int(info.levels)},
+              "clocks": clocks, "gpu_launches": int(info.kernel_launches), "roofline": roofline}
+
+    # ---- exact mode (bit-identical to the reference) -------------------------------------------------------------
+    if not args.no_exact:
+        ems, einfos, _ = timed_builds(vi.MODE_EXACT, 1, 2)
+        e_ms = sum(ems) / len(ems)
+        result["exact_mode"] = {"value": n / (e_ms / 1e3), "unit": "vectors/s", "ms_per_step": e_ms, "steps": 2, "warmup": 1,
+                                "note": "literal float32 sequential Welford (IndexBuilder.cs:175-197), bit-identical range table; "
+                                        "latency-bound by the per-(range,dim) recurrence at the top levels",
+                                "gpu_launches": int(einfos[-1].kernel_launches)}
+        log(f"exact build: {e_ms:.2f} ms/step")
+        ctx.build(vi.MODE_FAST)
+
+    # ---- search ---------------------------------------------------------------------------------------------------
+    if not args.no_search:
+        nq = args.queries
+        q_d = gen_queries(rows_d, nq, seed=77)
+        offs_d = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+        search = {}
+        for p in (0.0, 0.01):
+            total, visits = ctx.search_device(q_d.data_ptr(), nq, DIMS, p, offs_d.data_ptr(), 0, 0)
+            ids_out = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+            for _ in range(2):
+                ctx.search_device(q_d.data_ptr(), nq, DIMS, p, offs_d.data_ptr(), ids_out.data_ptr(), total)
+            torch.cuda.synchronize()
+            reps = 3
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                ctx.search_device(q_d.data_ptr(), nq, DIMS, p, offs_d.data_ptr(), ids_out.data_ptr(), total)
+            b.record(stream)
+            torch.cuda.synchronize()
+            sms = a.elapsed_time(b) / reps
+            bytes_q = nq * 4 * DIMS + 2 * visits * 16 + total * 8  # count pass + fill pass both walk the table
+            search[f"p={p}"] = {"queries_per_sec": nq / (sms / 1e3), "ms": sms, "queries": nq, "candidates": int(total),
+                                "visits": int(visits), "algorithmic_gbs": bytes_q / (sms / 1e3) / 1e9}
+            log(f"search p={p}: {sms:.2f} ms for {nq} queries, {total} candidates, {visits} visits")
+            del ids_out
+        result["search"] = search
+        del q_d, offs_d
+
+    # ---- e2e: host buffers through the C ABI ---------------------------------------------------------------------
+    rows_h = torch.empty((n, DIMS), dtype=torch.float32, pin_memory=True)
+    ids_h = torch.empty((n,), dtype=torch.int64, pin_memory=True)
+    rows_h.copy_(rows_d)
+    ids_h.copy_(ids_d)
+    torch.cuda.synchronize()
+    del rows_d, ids_d
+    ctx.close()
+    torch.cuda.empty_cache()
+    rows_np, ids_np = rows_h.numpy(), ids_h.numpy()
+    cap = 2 * n + n // 8 + 1024
+    out_rid = torch.empty(cap, dtype=torch.int64, pin_memory=True).numpy()
+    out_dim = torch.empty(cap, dtype=torch.int32, pin_memory=True).numpy()
+    out_mid = torch.empty(cap, dtype=torch.float32, pin_memory=True).numpy()
+    out_id = torch.empty(cap, dtype=torch.int64, pin_memory=True).numpy()
+    ctx = vi.Context(local)
+    e2e_ms = []
+    k_rows = 0
+    for i in range(2 + max(1, min(args.steps, 3))):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.reserve(n, DIMS)
+        ctx.add(ids_np, rows_np)
+        ctx.build(vi.MODE_FAST)
+        k_rows = ctx.ranges_into(out_rid, out_dim, out_mid, out_id)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= 2:
+            e2e_ms.append(dt)
+    e2e = sum(e2e_ms) / len(e2e_ms)
+    result["e2e"] = {"value": n / (e2e / 1e3), "unit": "vectors/s", "ms_per_step": e2e,
+                     "h2d_bytes_per_step": n * (4 * DIMS + 8), "d2h_bytes_per_step": int(k_rows) * 24,
+                     "steps": len(e2e_ms), "warmup": 2,
+                     "path": "vi_points_reserve + vi_points_add(host pinned) + vi_build(fast) + vi_ranges_copy(host pinned)"}
+    log(f"e2e: {e2e:.1f} ms/step")
+    ctx.close()
+
+    # ---- CPU baseline (reported, not the target) -------------------------------------------------------------------
+    if not args.no_cpu:
+        cb, _ = cpu_baseline(rows_np, ids_np, args.cpu_sample_rows)
+        result["cpu_baseline"] = cb
+        log(f"cpu baseline: {cb['value']:.0f} vectors/s ({cb['sample']})")
+    print(json.dumps(result), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,144 @@
+/*
+ * vi_b200.h -- C ABI of the B200-native split-tree vector index (libvi_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of nesterovsky-bros/vector-database: IndexBuilder.Build and the
+ * RangeID-0 -> Low/High traversal search.  The reference is 100 % managed C# + T-SQL and has no FFI of its own;
+ * each entry point below names the reference interface it replaces (paths relative to the reference root) and is
+ * what a P/Invoke layer would bind.  Signatures use only plain pointers, sizes and int status
+ * codes: no torch types, no exceptions, no callbacks on the hot path.
+ *
+ * Threading: one vi_ctx = one host thread ("instances of this class are not thread safe", MemoryRangeStore.cs:5).
+ * There is NO CPU fallback: every entry point that computes needs a CUDA device and fails with VI_ERR_CUDA when
+ * none is usable.
+ */
+#ifndef VI_B200_H
+#define VI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VI_ABI_VERSION 1
+
+/* Status codes.  The C# shim maps them back onto the reference's exception types. */
+enum
+{
+  VI_OK = 0,
+  VI_ERR_INVALID_ARG = 1,    /* ArgumentException("Invalid length of vector.") FileRangeStore.cs:59-64;
+                                ArgumentException("Invalid vector size.") MemoryVectorIndex.cs:254 */
+  VI_ERR_OVERFLOW = 2,       /* OverflowException from checked(rangeId*2+1|2) IndexBuilder.cs:99,104 (depth > 62) */
+  VI_ERR_NOT_IMPLEMENTED = 3,/* NotImplementedException, root RangeStore.Add IndexBuilder.cs:206-209 */
+  VI_ERR_STATE = 4,          /* call out of order (e.g. search before build) */
+  VI_ERR_CAPACITY = 5,       /* caller buffer or reserved capacity too small */
+  VI_ERR_OOM = 6,            /* device or host allocation failed */
+  VI_ERR_CUDA = 7            /* CUDA runtime error, text in vi_last_error */
+};
+
+/* Statistics modes of vi_build. */
+enum
+{
+  VI_MODE_EXACT = 0, /* literal float32 sequential Welford, IndexBuilder.cs:175-197: bit-identical range table */
+  VI_MODE_FAST = 1   /* q30: order-independent exact integer sums, HBM-bound, shardable */
+};
+
+typedef struct vi_ctx vi_ctx;
+
+/* Per-build counters (all levels). */
+typedef struct vi_build_info
+{
+  int64_t ranges;        /* rows in the range table */
+  int32_t levels;        /* tree levels processed (max depth + 1) */
+  int32_t mode;
+  int64_t point_visits;  /* sum over levels of points in non-leaf ranges (A_l) */
+  int64_t kernel_launches;
+  double build_ms;       /* device time of the whole build, CUDA events */
+  int32_t q30_exponent;  /* fast mode: E with max|x| < 2^E */
+  int32_t reserved;
+} vi_build_info;
+
+/* Per-level record (profiling / roofline accounting, Program.cs has only a whole-build Stopwatch). */
+typedef struct vi_level_info
+{
+  int32_t level;
+  int32_t reserved;
+  int64_t ranges;        /* non-leaf ranges processed at this level */
+  int64_t points;        /* points in them (A_l) */
+  int64_t rows_emitted;  /* table rows of this level (leaves included) */
+  double stats_ms, partition_ms;
+} vi_level_info;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+int vi_abi_version(void);
+/* device: CUDA ordinal.  Replaces nothing in the reference (it has no device); corresponds to constructing
+ * the store factory, `new FileRangeStore(count, dimensions)` FileRangeStore.cs:18-27. */
+int vi_create(int32_t device, vi_ctx** out);
+void vi_destroy(vi_ctx* ctx); /* FileRangeStore.Dispose FileRangeStore.cs:32 */
+const char* vi_last_error(const vi_ctx* ctx);
+
+/* ---- ingest: the batched IRangeStore.Add (IRangeStore.cs:15, FileRangeStore.cs:57-75) ------------------------ */
+/* Fixes the dimension count (FileRangeStore ctor arg `dimensions`) and reserves device memory for `capacity`
+ * points (ctor arg `count`). Drops previously added points and any built table. */
+int vi_points_reserve(vi_ctx* ctx, int64_t capacity, int32_t dims);
+/* Appends n points from HOST memory: ids[n], rows row-major n x dims float32.  The library copies (as
+ * FileRangeStore copies into its mapping, FileRangeStore.cs:140-151), so the caller's buffers are reusable on
+ * return.  Grows the reservation if needed.  `dims` must equal the reserved dimension count, otherwise
+ * VI_ERR_INVALID_ARG ("Invalid length of vector."). */
+int vi_points_add(vi_ctx* ctx, const int64_t* ids, const float* rows, int64_t n, int32_t dims);
+/* Same, from DEVICE memory on the ctx's device (device-to-device copy). */
+int vi_points_add_device(vi_ctx* ctx, const int64_t* d_ids, const float* d_rows, int64_t n, int32_t dims);
+int64_t vi_points_count(const vi_ctx* ctx);
+
+/* ---- build: IndexBuilder.Build (IndexBuilder.cs:23-157) ------------------------------------------------------ */
+/* Level-synchronous GPU build over every open range at once.  info may be NULL. */
+int vi_build(vi_ctx* ctx, int32_t mode, vi_build_info* info);
+/* Copies up to cap per-level records of the last build; returns the number of levels in *n. */
+int vi_build_levels(const vi_ctx* ctx, vi_level_info* out, int32_t cap, int32_t* n);
+
+/* ---- range table out: the (rangeId, RangeValue) stream of Build (IndexBuilder.cs:92, RangeValue.cs) ---------- */
+int64_t vi_range_count(const vi_ctx* ctx);
+/* Rows in breadth-first order, ascending rangeId inside a level.  Any output pointer may be NULL.
+ * dimension == -1 marks a leaf (RangeValue.Dimension), id is the leaf's point id there and the tie-break pivot
+ * elsewhere (RangeValue.Id). */
+int vi_ranges_copy(const vi_ctx* ctx, int64_t* range_id, int32_t* dimension, float* mid, int64_t* id, int64_t cap);
+/* dbo.TextIndex form (DDL.sql:209-227): child RangeIDs or -1 for null, TextID = id for leaves and -1 (null)
+ * for internal rows (DDL.sql:195-197), Dimension -1 / Mid NaN stand for null. */
+int vi_textindex_copy(const vi_ctx* ctx, int64_t* range_id, int16_t* dimension, float* mid, int64_t* low_range_id,
+                      int64_t* high_range_id, int64_t* text_id, int64_t cap);
+
+/* ---- search: dbo.Search (DDL.sql:234-295) behind the Find(vector, distance, predicate) shape
+ *      (MemoryVectorIndex.cs:242-245) ---------------------------------------------------------------------------- */
+/* Batched traversal of nq HOST queries (row-major nq x dims) with one proximity.  CSR result: offsets[nq+1] and
+ * ids (candidate TextIDs per query, DFS order, low branch first).  Two-call protocol: call with ids == NULL (or
+ * cap too small) to get *total and offsets, then with cap >= *total.  Returns VI_ERR_CAPACITY when ids != NULL
+ * and cap < *total (offsets and *total are still valid). */
+int vi_search(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int64_t* offsets,
+              int64_t* ids, int64_t cap, int64_t* total);
+/* Device-resident form: d_queries, d_offsets[nq+1], d_ids[cap] are device pointers; *total is a host value.
+ * visits (host, may be NULL) receives the number of table rows visited. */
+int vi_search_device(vi_ctx* ctx, const float* d_queries, int64_t nq, int32_t dims, float proximity,
+                     int64_t* d_offsets, int64_t* d_ids, int64_t cap, int64_t* total, int64_t* visits);
+/* Candidate verification, the `predicate` half of the Find contract (MemoryVectorIndex.cs:237-241, 336-342):
+ * keeps the candidates whose Euclidean distance to the query is <= distance (float32 sum in index order then
+ * sqrt, as MemoryVectorIndexTests.cs:209-217).  Same CSR two-call protocol as vi_search. */
+int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, float distance,
+                     int64_t* offsets, int64_t* ids, int64_t cap, int64_t* total);
+
+/* ---- multi-GPU (one process per GPU; the host supplies the collective, e.g. torch.distributed/NCCL) ----------- */
+/* Sum-all-reduce of `count` uint64 words in DEVICE memory `buf`, in place, across all ranks.  Called by
+ * vi_build (fast mode only) once per level while ranges are shared between ranks. */
+typedef int (*vi_allreduce_u64_fn)(void* user, void* d_buf, int64_t count);
+int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64_fn fn, void* user);
+
+/* ---- utilities -------------------------------------------------------------------------------------------------- */
+/* Raw device pointers of the built table for zero-copy consumers (valid until the next build/reserve/destroy). */
+int vi_table_device(const vi_ctx* ctx, const int64_t** range_id, const int32_t** dimension, const float** mid,
+                    const int64_t** id, const int32_t** low_row, const int32_t** high_row);
+/* CUDA stream (cudaStream_t) all work of this ctx is launched on; for external event timing. */
+void* vi_stream(const vi_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VI_B200_H */

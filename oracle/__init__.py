@@ -88,7 +88,7 @@ def build(ids: np.ndarray, rows: np.ndarray, mode: int = MODE_LITERAL) -> RangeT
     ids = np.ascontiguousarray(ids, dtype=np.int64)
     assert rows.ndim == 2 and ids.shape[0] == rows.shape[0]
     n, d = rows.shape
-    cap = 2 * n + 128  # 2n-1 rows normally; degenerate chains add < 64 per point
+    cap = 2 * n + n // 8 + 1024  # 2n-1 rows normally; a one-sided split adds a one-child row (same as the GPU table)
     rid = np.empty(cap, np.int64)
     dim = np.empty(cap, np.int32)
     mid = np.empty(cap, np.float32)

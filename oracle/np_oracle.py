@@ -110,11 +110,28 @@ def build_q30(ids, rows):
         s1 = [int(v) for v in sub.sum(axis=0)]
         s2 = [sum(int(v) * int(v) for v in sub[:, j]) for j in range(sub.shape[1])]
         keys = [n * b - a * a for a, b in zip(s1, s2)]
-        index = 0
-        for i in range(1, len(keys)):
-            if (keys[i] > keys[index]) if mx else (keys[i] < keys[index]):
-                index = i
-        mid = np.float32((np.float64(s1[index]) / np.float64(n)) * np.float64(2.0) ** (e - 30))
+        if max(keys) < (n * n) << 20:
+            # poorly resolved range: literal float32 Welford statistics (IndexBuilder.cs:159-197)
+            mean = rows[pts[0]].copy()
+            q = np.zeros_like(mean)
+            with np.errstate(all="ignore"):
+                for c, p in enumerate(pts[1:], start=2):
+                    v = rows[p]
+                    a = mean + (v - mean) / np.float32(c)
+                    q = q + (v - mean) * (v - a)
+                    mean = a
+            fk = q if mx else -q
+            index = 0
+            for i in range(1, len(fk)):
+                if _cmp_dotnet(fk[i], fk[index]) > 0:
+                    index = i
+            mid = mean[index]
+        else:
+            index = 0
+            for i in range(1, len(keys)):
+                if (keys[i] > keys[index]) if mx else (keys[i] < keys[index]):
+                    index = i
+            mid = np.float32((np.float64(s1[index]) / np.float64(n)) * np.float64(2.0) ** (e - 30))
         pivot = _trunc_div(idn, n)
         out.append((range_id, index, mid, pivot))
         lo, hi = [], []

@@ -44,6 +44,9 @@ typedef unsigned __int128 u128;
 #define VIO_ERR_NOMEM -3
 #define VIO_ERR_ARG -4
 
+/* q30 mode: a range is "resolved" when some dimension has n^2 * var >= n^2 * 2^(2*10) in quantised units */
+#define VIO_Q30_MIN_RES_BITS 10
+
 /* float.CompareTo as used by Comparer<float>.Default inside Enumerable.MaxBy (IndexBuilder.cs:77-79):
  * NaN sorts below every number, NaN == NaN, -0 == +0. */
 static inline int cmp_float_dotnet(float a, float b)
@@ -161,7 +164,39 @@ int vio_build(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float*
     int32_t index = 0;
     float mid = 0.0f;
 
-    if (mode == 0)
+    int literal = (mode == 0);
+    if (mode == 1)
+    {
+      /* q30 specification (DESIGN.md "fast mode"): exact integer sums of xi = rint(x * 2^(30-E)). */
+      for (int32_t i = 0; i < d; ++i) { s1[i] = 0; s2[i] = 0; }
+      for (int64_t j = 0; j < count; ++j)
+      {
+        const float* v = rows + p[j] * ld;
+        for (int32_t i = 0; i < d; ++i)
+        {
+          int64_t xi = q30_quantise(v[i], qk);
+          s1[i] += xi;
+          s2[i] += (u128)(uint64_t)(xi * xi);
+        }
+        idn += (i128)ids[p[j]];
+      }
+      /* key K = n*S2 - S1^2 (exact, >= 0); even depth argmax, odd depth argmin, lowest index wins ties */
+      u128 bestk = 0;
+      u128 thr = ((u128)(uint64_t)count * (u128)(uint64_t)count) << (2 * VIO_Q30_MIN_RES_BITS);
+      int resolved = 0;
+      for (int32_t i = 0; i < d; ++i)
+      {
+        i128 a = (i128)s1[i];
+        u128 k = (u128)(uint64_t)count * s2[i] - (u128)(a * a);
+        if (k >= thr) resolved = 1;
+        if (i == 0 || (it.max ? (k > bestk) : (k < bestk))) { bestk = k; index = i; }
+      }
+      mid = (float)(((double)s1[index] / (double)count) * qinv);
+      /* Poorly resolved range: no dimension spreads over 2^10 quantisation steps (stdev), so the integer
+       * statistics cannot separate its points; it takes the reference's own float32 statistics instead. */
+      if (!resolved) { literal = 1; idn = 0; index = 0; }
+    }
+    if (literal)
     {
       /* IndexBuilder.cs:159-173 InitStats */
       const float* v0 = rows + p[0] * ld;
@@ -192,31 +227,6 @@ int vio_build(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float*
         if (cmp_float_dotnet(key, best) > 0) { best = key; index = i; }
       }
       mid = mean[index];
-    }
-    else
-    {
-      /* q30 specification (DESIGN.md "fast mode"): exact integer sums of xi = rint(x * 2^(30-E)). */
-      for (int32_t i = 0; i < d; ++i) { s1[i] = 0; s2[i] = 0; }
-      for (int64_t j = 0; j < count; ++j)
-      {
-        const float* v = rows + p[j] * ld;
-        for (int32_t i = 0; i < d; ++i)
-        {
-          int64_t xi = q30_quantise(v[i], qk);
-          s1[i] += xi;
-          s2[i] += (u128)(uint64_t)(xi * xi);
-        }
-        idn += (i128)ids[p[j]];
-      }
-      /* key K = n*S2 - S1^2 (exact, >= 0); even depth argmax, odd depth argmin, lowest index wins ties */
-      u128 bestk = 0;
-      for (int32_t i = 0; i < d; ++i)
-      {
-        i128 a = (i128)s1[i];
-        u128 k = (u128)(uint64_t)count * s2[i] - (u128)(a * a);
-        if (i == 0 || (it.max ? (k > bestk) : (k < bestk))) { bestk = k; index = i; }
-      }
-      mid = (float)(((double)s1[index] / (double)count) * qinv);
     }
 
     if (emitted >= cap) { rc = VIO_ERR_CAPACITY; goto done; }

@@ -1,0 +1,228 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for both modes: exact mode vs the literal oracle, fast mode vs the q30 specification oracle."""
+import numpy as np
+import pytest
+
+import oracle
+import vectorindex as vi
+from vectorindex import synthetic as ds
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_table(ids, rows, mode):
+    with vi.Context(0) as ctx:
+        ctx.reserve(len(ids), rows.shape[1])
+        ctx.add(ids, rows)
+        info = ctx.build(mode)
+        rid, dim, mid, oid = ctx.ranges()
+    order = np.argsort(rid, kind="stable")
+    assert np.array_equal(order, np.arange(len(rid))), "rows must come sorted by rangeId (BFS order)"
+    return rid, dim, mid, oid, info
+
+
+def assert_same_table(ids, rows, mode):
+    rid, dim, mid, oid, info = gpu_table(ids, rows, mode)
+    ref = oracle.build(ids, rows, mode)
+    assert len(rid) == len(ref)
+    assert np.array_equal(rid, ref.range_id)
+    assert np.array_equal(dim, ref.dimension)
+    assert np.array_equal(mid.view(np.uint32), ref.mid.view(np.uint32)), "Mid must be bit-identical"
+    assert np.array_equal(oid, ref.id)
+    return info
+
+
+MODES = [vi.MODE_EXACT, vi.MODE_FAST]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n,d", [(1, 4), (2, 4), (3, 1), (5, 7), (33, 3), (600, 96), (1000, 33), (4097, 16)])
+def test_small_shapes(mode, n, d):
+    ids, rows = ds.uniform(n, d, seed=n + d)
+    ids = (ids * 7 + 3)
+    assert_same_table(ids, rows, mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_empty(mode):
+    with vi.Context(0) as ctx:
+        ctx.reserve(0, 8)
+        ctx.build(mode)
+        assert ctx.range_count == 0
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_config1_100k_x_96_uniform(mode):
+    # BASELINE.json configs[0]: MainTest-shaped build (Program.cs:163-181) at 100k x 96
+    ids, rows = ds.uniform(100_000, 96, seed=1)
+    info = assert_same_table(ids, rows, mode)
+    assert info.ranges == 2 * 100_000 - 1
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_unit_gaussian_50k_x_96(mode):
+    ids, rows = ds.unit_gaussian(50_000, 96, seed=2)
+    assert_same_table(ids, rows, mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_wide_rows_768(mode):
+    # configs[4] shape (text-embedding width), reduced count
+    ids, rows = ds.unit_gaussian(6000, 768, seed=3)
+    assert_same_table(ids, rows, mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_one_hot_crafted_set(mode):
+    # Program.cs:54-66; literal mode must pick dimension 3 at the root, q30 dimension 0
+    ids, rows = ds.one_hot(1536)
+    rid, dim, mid, oid, _ = gpu_table(ids, rows, mode)
+    assert dim[0] == (3 if mode == vi.MODE_EXACT else 0)
+    assert_same_table(ids, rows, mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_duplicates_constant_columns_negative_ids(mode):
+    rng = np.random.default_rng(9)
+    base = rng.random((700, 12), dtype=np.float32)
+    rows = np.concatenate([base, base, base], 0)
+    rows[:, 5] = 0.125
+    ids = (np.arange(2100, dtype=np.int64)[::-1] - 1000) * 1_000_000_007
+    assert_same_table(ids, rows, mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_scaled_data(mode):
+    ids, rows = ds.uniform(5000, 20, seed=11)
+    assert_same_table(ids, (rows * np.float32(1e4)).astype(np.float32), mode)
+    assert_same_table(ids, (rows * np.float32(1e-5)).astype(np.float32), mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_skewed_tree(mode):
+    # exponential spread: very unbalanced splits, deep tree, big and tiny ranges on the same level
+    rng = np.random.default_rng(4)
+    rows = np.exp(rng.standard_normal((20000, 6)) * 3).astype(np.float32)
+    ids = np.arange(20000, dtype=np.int64)
+    assert_same_table(ids, rows, mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_inseparable_points_overflow(mode):
+    # same vector, same id: never separate -> OverflowException at depth 62 (IndexBuilder.cs:99)
+    rows = np.full((2, 3), 0.5, np.float32)
+    ids = np.array([-4, -5], np.int64)
+    with vi.Context(0) as ctx:
+        ctx.reserve(2, 3)
+        ctx.add(ids, rows)
+        with pytest.raises(OverflowError):
+            ctx.build(mode)
+
+
+def test_wrong_vector_length_is_argument_error():
+    with vi.Context(0) as ctx:
+        ctx.reserve(4, 8)
+        with pytest.raises(ValueError, match="Invalid length of vector"):
+            ctx.add(np.arange(4), np.zeros((4, 7), np.float32))
+
+
+def test_incremental_add_equals_single_add():
+    ids, rows = ds.uniform(3000, 10, seed=5)
+    with vi.Context(0) as ctx:
+        ctx.reserve(10, 10)  # forces growth
+        for s in range(0, 3000, 700):
+            ctx.add(ids[s:s + 700], rows[s:s + 700])
+        ctx.build(vi.MODE_EXACT)
+        rid, dim, mid, oid = ctx.ranges()
+    ref = oracle.build(ids, rows, oracle.MODE_LITERAL)
+    assert np.array_equal(rid, ref.range_id) and np.array_equal(dim, ref.dimension)
+    assert np.array_equal(mid.view(np.uint32), ref.mid.view(np.uint32)) and np.array_equal(oid, ref.id)
+
+
+def test_index_builder_mirror_yields_reference_rows():
+    ids, rows = ds.uniform(500, 5, seed=8)
+    pts = [(int(i), rows[k]) for k, i in enumerate(ids)]
+    got = dict(vi.IndexBuilder.Build(pts, lambda rangeId, capacity: vi.MemoryRangeStore()))
+    ref = oracle.build(ids, rows).as_dict()
+    assert got.keys() == ref.keys()
+    for k, v in got.items():
+        assert (v.Dimension, v.Id) == (ref[k][0], ref[k][2])
+        assert np.float32(v.Mid).tobytes() == np.float32(ref[k][1]).tobytes()
+
+
+# ---- search ------------------------------------------------------------------------------------------------------
+def _sorted_sets(offs, ids):
+    return [np.sort(ids[offs[i]:offs[i + 1]]) for i in range(len(offs) - 1)]
+
+
+@pytest.mark.parametrize("p", [0.0, 0.01, 0.05, 0.2])
+def test_search_matches_oracle_traversal(p):
+    ids, rows = ds.unit_gaussian(30_000, 96, seed=2)
+    _, fresh = ds.unit_gaussian(300, 96, seed=77)
+    queries = np.concatenate([rows[:300], fresh], 0)
+    with vi.Context(0) as ctx:
+        ctx.reserve(len(ids), 96)
+        ctx.add(ids, rows)
+        ctx.build(vi.MODE_EXACT)
+        offs, out = ctx.search(queries, p)
+    ref = oracle.build(ids, rows)
+    roffs, rout, _ = oracle.search(ref, queries, p)
+    assert np.array_equal(offs, roffs)
+    assert np.array_equal(out, rout)  # same DFS order, not only the same sets
+    if p == 0.0:
+        for i in range(300):
+            assert ids[i] in out[offs[i]:offs[i + 1]]
+
+
+def test_search_verify_equals_bruteforce():
+    # MemoryVectorIndexTests.cs:161-204 property: Find + Euclidean predicate == brute force
+    ids, rows = ds.grid2d(100)
+    q = np.array([[0.1, -0.3], [0.9, 0.9], [-1.0, 0.0]], np.float32)
+    dist = 0.07
+    with vi.Context(0) as ctx:
+        ctx.reserve(len(ids), 2)
+        ctx.add(ids, rows)
+        ctx.build(vi.MODE_EXACT)
+        offs, out = ctx.search_verify(q, dist, dist)
+    for i in range(q.shape[0]):
+        want = sorted(int(k) for k in ids if oracle.distance_l2(rows[k], q[i]) <= np.float32(dist))
+        assert sorted(out[offs[i]:offs[i + 1]].tolist()) == want
+        assert len(want) > 0
+
+
+def test_find_entry_point_shape():
+    ids, rows = ds.grid2d(40)
+    index = vi.VectorIndex(ids, rows)
+    q = np.array([0.2, 0.2], np.float32)
+    dist = 0.1
+    calls = []
+
+    def predicate(i, v):
+        calls.append(i)
+        return oracle.distance_l2(v, q) <= np.float32(dist)
+
+    got = sorted(index.Find(q, dist, predicate))
+    want = sorted(int(k) for k in ids if oracle.distance_l2(rows[k], q) <= np.float32(dist))
+    assert got == want and len(calls) >= len(want)
+    assert sorted(index.Find(q, dist)) == want
+    with pytest.raises(ValueError, match="Invalid vector size"):
+        list(index.Find(np.zeros(3, np.float32), dist))
+    index.close()
+
+
+def test_textindex_rows():
+    ids, rows = ds.uniform(200, 4, seed=3)
+    with vi.Context(0) as ctx:
+        ctx.reserve(200, 4)
+        ctx.add(ids, rows)
+        ctx.build(vi.MODE_EXACT)
+        rid, dim, mid, lo, hi, tid = ctx.textindex()
+    have = set(rid.tolist())
+    for k in range(len(rid)):
+        if dim[k] < 0:
+            assert tid[k] >= 0 and lo[k] == -1 and hi[k] == -1 and np.isnan(mid[k])
+        else:
+            assert tid[k] == -1
+            assert lo[k] in (-1, 2 * rid[k] + 1) and hi[k] in (-1, 2 * rid[k] + 2)
+            assert (lo[k] == -1) == (2 * rid[k] + 1 not in have)
+            assert (hi[k] == -1) == (2 * rid[k] + 2 not in have)

@@ -1,0 +1,365 @@
+// vi_abi.cu -- the extern "C" boundary declared in include/vi_b200.h.  Host-side bookkeeping only; all compute is in
+// vi_build.cu / vi_search.cu.  There is no CPU fallback anywhere: without a usable CUDA device vi_create fails.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+
+#include "vi_common.cuh"
+
+static const char* kNullCtx = "null context";
+
+template <typename T>
+static int grow(vi_ctx* ctx, T** buf, int64_t* cap, int64_t need)
+{
+  if (*cap >= need && *buf) return VI_OK;
+  cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  int64_t ncap = need + need / 4 + 256;
+  VI_CUDA_TRY(cudaMalloc((void**)buf, (size_t)ncap * sizeof(T)));
+  *cap = ncap;
+  return VI_OK;
+}
+
+extern "C" {
+
+int vi_abi_version(void) { return VI_ABI_VERSION; }
+
+int vi_create(int32_t device, vi_ctx** out)
+{
+  if (!out) return VI_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+  {
+    cudaGetLastError();
+    return VI_ERR_CUDA;  // no CPU fallback
+  }
+  vi_ctx* ctx = new (std::nothrow) vi_ctx();
+  if (!ctx) return VI_ERR_OOM;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->counters, 256) != cudaSuccess)
+  {
+    cudaGetLastError();
+    delete ctx;
+    return VI_ERR_CUDA;
+  }
+  cudaMemset(ctx->counters, 0, 256);
+  *out = ctx;
+  return VI_OK;
+}
+
+static void free_points(vi_ctx* ctx)
+{
+  cudaFree(ctx->rows); ctx->rows = nullptr;
+  cudaFree(ctx->ids); ctx->ids = nullptr;
+  ctx->capacity = 0;
+  ctx->n = 0;
+}
+
+void vi_destroy(vi_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  vi_free_workspace(ctx);
+  vi_free_table(ctx);
+  free_points(ctx);
+  cudaFree(ctx->q_buf); cudaFree(ctx->off_buf); cudaFree(ctx->ids_buf); cudaFree(ctx->off2_buf);
+  cudaFree(ctx->ids2_buf); cudaFree(ctx->search_src); cudaFree(ctx->verify_keep);
+  cudaFree(ctx->counters);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* vi_last_error(const vi_ctx* ctx) { return ctx ? ctx->err.c_str() : kNullCtx; }
+
+static int reserve_points(vi_ctx* ctx, int64_t capacity)
+{
+  // grows the point store, keeping the points already added
+  if (capacity <= ctx->capacity && ctx->rows) return VI_OK;
+  float* nrows = nullptr;
+  i64* nids = nullptr;
+  const size_t rbytes = (size_t)capacity * ctx->ld * sizeof(float) + 256;
+  VI_CUDA_TRY(cudaMalloc((void**)&nrows, rbytes));
+  cudaError_t e = cudaMalloc((void**)&nids, (size_t)capacity * sizeof(i64) + 256);
+  if (e != cudaSuccess) { cudaFree(nrows); return ctx->fail_cuda(e, "cudaMalloc(ids)", __FILE__, __LINE__); }
+  if (ctx->n > 0)
+  {
+    cudaMemcpyAsync(nrows, ctx->rows, (size_t)ctx->n * ctx->ld * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(nids, ctx->ids, (size_t)ctx->n * sizeof(i64), cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(ctx->rows);
+  cudaFree(ctx->ids);
+  ctx->rows = nrows;
+  ctx->ids = nids;
+  ctx->capacity = capacity;
+  return VI_OK;
+}
+
+int vi_points_reserve(vi_ctx* ctx, int64_t capacity, int32_t dims)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (capacity < 0 || dims <= 0 || dims > 32767)  // `short dimensions`, FileRangeStore.cs:18
+    return ctx->fail(VI_ERR_INVALID_ARG, "Invalid capacity or dimensions.");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  free_points(ctx);
+  vi_free_table(ctx);
+  vi_free_workspace(ctx);
+  ctx->dims = dims;
+  ctx->ld = (dims + 3) & ~3;
+  if (capacity == 0) return VI_OK;
+  return reserve_points(ctx, capacity);
+}
+
+static int add_points(vi_ctx* ctx, const int64_t* ids, const float* rows, int64_t n, int32_t dims, cudaMemcpyKind kind)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (ctx->dims == 0) return ctx->fail(VI_ERR_STATE, "vi_points_reserve must be called first");
+  if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid length of vector.");  // FileRangeStore.cs:59-64
+  if (n < 0 || (n > 0 && (!ids || !rows))) return ctx->fail(VI_ERR_INVALID_ARG, "null points");
+  if (n == 0) return VI_OK;
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (ctx->n + n > ctx->capacity)
+  {
+    int64_t want = ctx->capacity * 2;
+    if (want < ctx->n + n) want = ctx->n + n;
+    int rc = reserve_points(ctx, want);
+    if (rc != VI_OK) return rc;
+  }
+  ctx->built = false;
+  float* dst = ctx->rows + (size_t)ctx->n * ctx->ld;
+  if (ctx->ld == dims)
+    VI_CUDA_TRY(cudaMemcpyAsync(dst, rows, (size_t)n * dims * sizeof(float), kind, ctx->stream));
+  else
+  {
+    VI_CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)n * ctx->ld * sizeof(float), ctx->stream));
+    VI_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ctx->ld * sizeof(float), rows, (size_t)dims * sizeof(float),
+                                  (size_t)dims * sizeof(float), (size_t)n, kind, ctx->stream));
+  }
+  VI_CUDA_TRY(cudaMemcpyAsync(ctx->ids + ctx->n, ids, (size_t)n * sizeof(i64), kind, ctx->stream));
+  VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // caller's buffers are reusable on return
+  ctx->n += n;
+  return VI_OK;
+}
+
+int vi_points_add(vi_ctx* ctx, const int64_t* ids, const float* rows, int64_t n, int32_t dims)
+{
+  return add_points(ctx, ids, rows, n, dims, cudaMemcpyHostToDevice);
+}
+
+int vi_points_add_device(vi_ctx* ctx, const int64_t* d_ids, const float* d_rows, int64_t n, int32_t dims)
+{
+  return add_points(ctx, d_ids, d_rows, n, dims, cudaMemcpyDeviceToDevice);
+}
+
+int64_t vi_points_count(const vi_ctx* ctx) { return ctx ? ctx->n : 0; }
+
+int vi_build(vi_ctx* ctx, int32_t mode, vi_build_info* info)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (mode != VI_MODE_EXACT && mode != VI_MODE_FAST) return ctx->fail(VI_ERR_INVALID_ARG, "unknown build mode");
+  if (ctx->dims == 0) return ctx->fail(VI_ERR_STATE, "no points: vi_points_reserve / vi_points_add first");
+  if (ctx->world > 1 && mode != VI_MODE_FAST)
+    return ctx->fail(VI_ERR_INVALID_ARG, "multi-rank build needs VI_MODE_FAST (order-independent sums)");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc = vi_build_impl(ctx, mode);
+  if (info) *info = ctx->info;
+  return rc;
+}
+
+int vi_build_levels(const vi_ctx* ctx, vi_level_info* out, int32_t cap, int32_t* n)
+{
+  if (!ctx || !n) return VI_ERR_INVALID_ARG;
+  *n = (int32_t)ctx->levels.size();
+  if (out)
+    for (int32_t i = 0; i < *n && i < cap; ++i) out[i] = ctx->levels[i];
+  return VI_OK;
+}
+
+int64_t vi_range_count(const vi_ctx* ctx) { return (ctx && ctx->built) ? ctx->t_rows : 0; }
+
+int vi_ranges_copy(const vi_ctx* cctx, int64_t* range_id, int32_t* dimension, float* mid, int64_t* id, int64_t cap)
+{
+  vi_ctx* ctx = const_cast<vi_ctx*>(cctx);
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  const int64_t k = ctx->t_rows;
+  if (cap < k) return ctx->fail(VI_ERR_CAPACITY, "range buffers too small");
+  if (k == 0) return VI_OK;
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (range_id) VI_CUDA_TRY(cudaMemcpyAsync(range_id, ctx->t_rid, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+  if (dimension) VI_CUDA_TRY(cudaMemcpyAsync(dimension, ctx->t_dim, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+  if (mid) VI_CUDA_TRY(cudaMemcpyAsync(mid, ctx->t_mid, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+  if (id) VI_CUDA_TRY(cudaMemcpyAsync(id, ctx->t_id, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaStreamSynchronize(st));
+  return VI_OK;
+}
+
+int vi_textindex_copy(const vi_ctx* cctx, int64_t* range_id, int16_t* dimension, float* mid, int64_t* low_range_id,
+                      int64_t* high_range_id, int64_t* text_id, int64_t cap)
+{
+  vi_ctx* ctx = const_cast<vi_ctx*>(cctx);
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  const int64_t k = ctx->t_rows;
+  if (cap < k) return ctx->fail(VI_ERR_CAPACITY, "range buffers too small");
+  if (k == 0) return VI_OK;
+  std::vector<i64> rid((size_t)k), id((size_t)k);
+  std::vector<int> dim((size_t)k), lo((size_t)k), hi((size_t)k);
+  std::vector<float> m((size_t)k);
+  int rc = vi_ranges_copy(ctx, rid.data(), dim.data(), m.data(), id.data(), k);
+  if (rc != VI_OK) return rc;
+  VI_CUDA_TRY(cudaMemcpy(lo.data(), ctx->t_low, (size_t)k * 4, cudaMemcpyDeviceToHost));
+  VI_CUDA_TRY(cudaMemcpy(hi.data(), ctx->t_high, (size_t)k * 4, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < k; ++i)
+  {
+    const bool leaf = dim[i] < 0;
+    if (range_id) range_id[i] = rid[i];
+    if (dimension) dimension[i] = leaf ? (int16_t)-1 : (int16_t)dim[i];
+    if (mid) mid[i] = leaf ? NAN : m[i];
+    if (low_range_id) low_range_id[i] = lo[i] >= 0 ? rid[lo[i]] : -1;
+    if (high_range_id) high_range_id[i] = hi[i] >= 0 ? rid[hi[i]] : -1;
+    if (text_id) text_id[i] = leaf ? id[i] : -1;  // DDL.sql:195-197: internal rows carry no TextID
+  }
+  return VI_OK;
+}
+
+int vi_search_device(vi_ctx* ctx, const float* d_queries, int64_t nq, int32_t dims, float proximity, int64_t* d_offsets,
+                     int64_t* d_ids, int64_t cap, int64_t* total, int64_t* visits)
+{
+  if (!ctx || !total) return VI_ERR_INVALID_ARG;
+  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");  // MemoryVectorIndex.cs:254
+  if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !d_queries) || !d_offsets)
+    return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  int* keep_src = ctx->search_src;
+  ctx->search_src = nullptr;  // plain search does not record source rows
+  int rc = vi_search_impl(ctx, d_queries, nq, proximity, d_offsets, d_ids, cap, total, visits, false);
+  ctx->search_src = keep_src;
+  return rc;
+}
+
+static int stage_queries(vi_ctx* ctx, const float* queries, int64_t nq)
+{
+  int rc = grow(ctx, &ctx->q_buf, &ctx->q_cap, nq * ctx->dims + 4);
+  if (rc != VI_OK) return rc;
+  rc = grow(ctx, &ctx->off_buf, &ctx->off_cap, nq + 2);
+  if (rc != VI_OK) return rc;
+  if (nq > 0)
+    VI_CUDA_TRY(cudaMemcpyAsync(ctx->q_buf, queries, (size_t)nq * ctx->dims * sizeof(float), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  return VI_OK;
+}
+
+int vi_search(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int64_t* offsets,
+              int64_t* ids, int64_t cap, int64_t* total)
+{
+  if (!ctx || !total || !offsets) return VI_ERR_INVALID_ARG;
+  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");
+  if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !queries)) return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc = stage_queries(ctx, queries, nq);
+  if (rc != VI_OK) return rc;
+  int* keep_src = ctx->search_src;
+  ctx->search_src = nullptr;
+  // count pass
+  rc = vi_search_impl(ctx, ctx->q_buf, nq, proximity, ctx->off_buf, nullptr, 0, total, nullptr, false);
+  if (rc == VI_OK)
+  {
+    VI_CUDA_TRY(cudaMemcpyAsync(offsets, ctx->off_buf, (size_t)(nq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ids)
+    {
+      if (cap < *total) rc = ctx->fail(VI_ERR_CAPACITY, "ids capacity smaller than the number of candidates");
+      else if (*total > 0)
+      {
+        rc = grow(ctx, &ctx->ids_buf, &ctx->ids_cap, *total);
+        if (rc == VI_OK) rc = vi_search_impl(ctx, ctx->q_buf, nq, proximity, ctx->off_buf, ctx->ids_buf, *total, total, nullptr, true);
+        if (rc == VI_OK)
+        {
+          VI_CUDA_TRY(cudaMemcpyAsync(ids, ctx->ids_buf, (size_t)*total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+          VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        }
+      }
+    }
+  }
+  ctx->search_src = keep_src;
+  return rc;
+}
+
+int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, float distance,
+                     int64_t* offsets, int64_t* ids, int64_t cap, int64_t* total)
+{
+  if (!ctx || !total || !offsets) return VI_ERR_INVALID_ARG;
+  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");
+  if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !queries)) return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc = stage_queries(ctx, queries, nq);
+  if (rc != VI_OK) return rc;
+  int64_t cand = 0;
+  int* keep_src = ctx->search_src;
+  ctx->search_src = nullptr;
+  rc = vi_search_impl(ctx, ctx->q_buf, nq, proximity, ctx->off_buf, nullptr, 0, &cand, nullptr, false);
+  ctx->search_src = keep_src;
+  if (rc != VI_OK) return rc;
+  rc = grow(ctx, &ctx->ids_buf, &ctx->ids_cap, cand + 1);
+  if (rc == VI_OK) rc = grow(ctx, &ctx->search_src, &ctx->src_cap, cand + 1);
+  if (rc == VI_OK) rc = grow(ctx, &ctx->verify_keep, &ctx->keep_cap, cand + 2);
+  if (rc == VI_OK) rc = grow(ctx, &ctx->off2_buf, &ctx->off2_cap, nq + 2);
+  if (rc == VI_OK) rc = grow(ctx, &ctx->ids2_buf, &ctx->ids2_cap, cand + 1);
+  if (rc != VI_OK) return rc;
+  rc = vi_search_impl(ctx, ctx->q_buf, nq, proximity, ctx->off_buf, ctx->ids_buf, cand, &cand, nullptr, true);
+  if (rc != VI_OK) return rc;
+  rc = vi_verify_impl(ctx, ctx->q_buf, nq, distance, ctx->off_buf, ctx->ids_buf, cand, ctx->off2_buf,
+                      ids ? ctx->ids2_buf : nullptr, total);
+  if (rc != VI_OK) return rc;
+  VI_CUDA_TRY(cudaMemcpyAsync(offsets, ctx->off2_buf, (size_t)(nq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ids)
+  {
+    if (cap < *total) return ctx->fail(VI_ERR_CAPACITY, "ids capacity smaller than the number of matches");
+    if (*total > 0)
+    {
+      VI_CUDA_TRY(cudaMemcpyAsync(ids, ctx->ids2_buf, (size_t)*total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  return VI_OK;
+}
+
+int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64_fn fn, void* user)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return ctx->fail(VI_ERR_INVALID_ARG, "bad collective");
+  ctx->rank = rank;
+  ctx->world = world;
+  ctx->allreduce = fn;
+  ctx->allreduce_user = user;
+  return VI_OK;
+}
+
+int vi_table_device(const vi_ctx* ctx, const int64_t** range_id, const int32_t** dimension, const float** mid,
+                    const int64_t** id, const int32_t** low_row, const int32_t** high_row)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (!ctx->built) return VI_ERR_STATE;
+  if (range_id) *range_id = ctx->t_rid;
+  if (dimension) *dimension = ctx->t_dim;
+  if (mid) *mid = ctx->t_mid;
+  if (id) *id = ctx->t_id;
+  if (low_row) *low_row = ctx->t_low;
+  if (high_row) *high_row = ctx->t_high;
+  return VI_OK;
+}
+
+void* vi_stream(const vi_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+}  // extern "C"

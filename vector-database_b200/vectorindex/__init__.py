@@ -1,0 +1,458 @@
+"""Host-side mirror of NesterovskyBros.VectorIndex over the libvi_b200 C ABI (include/vi_b200.h).
+
+Same names, argument meaning and error behaviour as the reference's C# surface for the split-tree path:
+
+  IndexBuilder.Build(points, storeFactory)   VectorIndex/IndexBuilder.cs:23-25
+  IRangeStore / MemoryRangeStore             VectorIndex/IRangeStore.cs:6-22, MemoryRangeStore.cs:7-32
+  FileRangeStore(count, dimensions, buffer)  VectorIndex/FileRangeStore.cs:18, .NextStore :40-43
+  RangeValue(Dimension, Mid, Id)             VectorIndex/RangeValue.cs:6-22
+  VectorIndex.Find(vector, distance, predicate)  shape of MemoryVectorIndex.cs:242-245 over dbo.Search (DDL.sql:234-295)
+
+All arithmetic happens in CUDA kernels behind the C ABI; this module only stages buffers.  There is no CPU
+fallback: importing works anywhere, but the first call that needs the library raises if libvi_b200.so or a CUDA
+device is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+from typing import Callable, Iterable, Iterator, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libvi_b200.so")
+
+VI_OK, VI_ERR_INVALID_ARG, VI_ERR_OVERFLOW, VI_ERR_NOT_IMPLEMENTED, VI_ERR_STATE, VI_ERR_CAPACITY, VI_ERR_OOM, \
+    VI_ERR_CUDA = range(8)
+MODE_EXACT = 0
+MODE_FAST = 1
+
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i16p = ctypes.POINTER(ctypes.c_int16)
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+class BuildInfo(ctypes.Structure):
+    _fields_ = [("ranges", ctypes.c_int64), ("levels", ctypes.c_int32), ("mode", ctypes.c_int32),
+                ("point_visits", ctypes.c_int64), ("kernel_launches", ctypes.c_int64), ("build_ms", ctypes.c_double),
+                ("q30_exponent", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class LevelInfo(ctypes.Structure):
+    _fields_ = [("level", ctypes.c_int32), ("reserved", ctypes.c_int32), ("ranges", ctypes.c_int64),
+                ("points", ctypes.c_int64), ("rows_emitted", ctypes.c_int64), ("stats_ms", ctypes.c_double),
+                ("partition_ms", ctypes.c_double)]
+
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
+
+# every symbol include/vi_b200.h declares
+EXPORTS = ["vi_abi_version", "vi_create", "vi_destroy", "vi_last_error", "vi_points_reserve", "vi_points_add",
+           "vi_points_add_device", "vi_points_count", "vi_build", "vi_build_levels", "vi_range_count",
+           "vi_ranges_copy", "vi_textindex_copy", "vi_search", "vi_search_device", "vi_search_verify",
+           "vi_set_collective", "vi_table_device", "vi_stream"]
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads libvi_b200.so (built in-tree by csrc/Makefile).  Raises if it is missing: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           f"(make -C vector-database_b200/csrc). There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp = ctypes.c_void_p
+    L.vi_abi_version.restype = ctypes.c_int
+    L.vi_create.argtypes = [ctypes.c_int32, ctypes.POINTER(vp)]
+    L.vi_destroy.argtypes = [vp]
+    L.vi_destroy.restype = None
+    L.vi_last_error.argtypes = [vp]
+    L.vi_last_error.restype = ctypes.c_char_p
+    L.vi_points_reserve.argtypes = [vp, ctypes.c_int64, ctypes.c_int32]
+    L.vi_points_add.argtypes = [vp, _i64p, _f32p, ctypes.c_int64, ctypes.c_int32]
+    L.vi_points_add_device.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int32]
+    L.vi_points_count.argtypes = [vp]
+    L.vi_points_count.restype = ctypes.c_int64
+    L.vi_build.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(BuildInfo)]
+    L.vi_build_levels.argtypes = [vp, ctypes.POINTER(LevelInfo), ctypes.c_int32, _i32p]
+    L.vi_range_count.argtypes = [vp]
+    L.vi_range_count.restype = ctypes.c_int64
+    L.vi_ranges_copy.argtypes = [vp, _i64p, _i32p, _f32p, _i64p, ctypes.c_int64]
+    L.vi_textindex_copy.argtypes = [vp, _i64p, _i16p, _f32p, _i64p, _i64p, _i64p, ctypes.c_int64]
+    L.vi_search.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, _i64p, _i64p, ctypes.c_int64,
+                            _i64p]
+    L.vi_search_device.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, vp, vp, ctypes.c_int64,
+                                   _i64p, _i64p]
+    L.vi_search_verify.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_float, _i64p,
+                                   _i64p, ctypes.c_int64, _i64p]
+    L.vi_set_collective.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ALLREDUCE_FN, vp]
+    L.vi_table_device.argtypes = [vp] + [ctypes.POINTER(vp)] * 6
+    L.vi_stream.argtypes = [vp]
+    L.vi_stream.restype = vp
+    for name in EXPORTS:
+        if name not in ("vi_destroy", "vi_last_error", "vi_points_count", "vi_range_count", "vi_stream",
+                        "vi_abi_version"):
+            getattr(L, name).restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+class VectorIndexError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"vi_b200 error {code}: {message}")
+        self.code = code
+
+
+def _raise(code: int, message: str):
+    """Maps C-ABI status codes back onto the reference's exception types (SURVEY.md 8b 'Errors')."""
+    if code == VI_ERR_INVALID_ARG:
+        raise ValueError(message)  # ArgumentException
+    if code == VI_ERR_OVERFLOW:
+        raise OverflowError(message)  # OverflowException, IndexBuilder.cs:99,104
+    if code == VI_ERR_NOT_IMPLEMENTED:
+        raise NotImplementedError(message)  # IndexBuilder.cs:206-209
+    if code == VI_ERR_OOM:
+        raise MemoryError(message)
+    raise VectorIndexError(code, message)
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+@dataclass(frozen=True)
+class RangeValue:
+    """VectorIndex/RangeValue.cs:6-22."""
+    Dimension: int
+    Mid: float
+    Id: int
+
+
+class Context:
+    """Thin owner of one vi_ctx (one CUDA device, one host thread)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = ctypes.c_void_p()
+        rc = self._L.vi_create(device, ctypes.byref(h))
+        if rc != VI_OK:
+            raise VectorIndexError(rc, "vi_create failed: no usable CUDA device (there is no CPU fallback)")
+        self._h = h
+        self.dims = 0
+        self._cb = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != VI_OK:
+            _raise(rc, self._L.vi_last_error(self._h).decode())
+
+    # ---- ingest ----
+    def reserve(self, capacity: int, dims: int):
+        self._check(self._L.vi_points_reserve(self._h, capacity, dims))
+        self.dims = dims
+
+    def add(self, ids: np.ndarray, rows: np.ndarray):
+        ids = np.ascontiguousarray(ids, np.int64)
+        rows = np.ascontiguousarray(rows, np.float32)
+        if rows.ndim != 2 or ids.shape[0] != rows.shape[0]:
+            raise ValueError("Invalid length of vector.")
+        self._check(self._L.vi_points_add(self._h, _p(ids, _i64p), _p(rows, _f32p), rows.shape[0], rows.shape[1]))
+
+    def add_device(self, d_ids_ptr: int, d_rows_ptr: int, n: int, dims: int):
+        self._check(self._L.vi_points_add_device(self._h, d_ids_ptr, d_rows_ptr, n, dims))
+
+    @property
+    def count(self) -> int:
+        return int(self._L.vi_points_count(self._h))
+
+    # ---- build ----
+    def build(self, mode: int = MODE_EXACT) -> BuildInfo:
+        info = BuildInfo()
+        self._check(self._L.vi_build(self._h, mode, ctypes.byref(info)))
+        return info
+
+    def levels(self):
+        n = ctypes.c_int32(0)
+        self._check(self._L.vi_build_levels(self._h, None, 0, ctypes.byref(n)))
+        arr = (LevelInfo * max(n.value, 1))()
+        self._check(self._L.vi_build_levels(self._h, arr, n.value, ctypes.byref(n)))
+        return [arr[i] for i in range(n.value)]
+
+    @property
+    def range_count(self) -> int:
+        return int(self._L.vi_range_count(self._h))
+
+    def ranges(self):
+        """(rangeId, Dimension, Mid, Id) columns in breadth-first order."""
+        k = self.range_count
+        rid = np.empty(k, np.int64)
+        dim = np.empty(k, np.int32)
+        mid = np.empty(k, np.float32)
+        oid = np.empty(k, np.int64)
+        self._check(self._L.vi_ranges_copy(self._h, _p(rid, _i64p), _p(dim, _i32p), _p(mid, _f32p), _p(oid, _i64p), k))
+        return rid, dim, mid, oid
+
+    def ranges_into(self, rid: np.ndarray, dim: np.ndarray, mid: np.ndarray, oid: np.ndarray) -> int:
+        """Same as ranges() into caller-owned (e.g. pinned) arrays; returns the row count."""
+        k = self.range_count
+        self._check(self._L.vi_ranges_copy(self._h, _p(rid, _i64p), _p(dim, _i32p), _p(mid, _f32p), _p(oid, _i64p),
+                                           min(rid.shape[0], dim.shape[0], mid.shape[0], oid.shape[0])))
+        return k
+
+    def textindex(self):
+        """dbo.TextIndex columns (DDL.sql:209-227): RangeID, Dimension, Mid, LowRangeID, HighRangeID, TextID."""
+        k = self.range_count
+        rid = np.empty(k, np.int64)
+        dim = np.empty(k, np.int16)
+        mid = np.empty(k, np.float32)
+        lo = np.empty(k, np.int64)
+        hi = np.empty(k, np.int64)
+        tid = np.empty(k, np.int64)
+        self._check(self._L.vi_textindex_copy(self._h, _p(rid, _i64p), _p(dim, _i16p), _p(mid, _f32p), _p(lo, _i64p),
+                                              _p(hi, _i64p), _p(tid, _i64p), k))
+        return rid, dim, mid, lo, hi, tid
+
+    # ---- search ----
+    def search(self, queries: np.ndarray, proximity: float):
+        """Batched dbo.Search. Returns CSR (offsets[nq+1], ids)."""
+        queries = np.ascontiguousarray(queries, np.float32)
+        if queries.ndim == 1:
+            queries = queries[None, :]
+        nq, d = queries.shape
+        offsets = np.zeros(nq + 1, np.int64)
+        total = ctypes.c_int64(0)
+        rc = self._L.vi_search(self._h, _p(queries, _f32p), nq, d, ctypes.c_float(proximity), _p(offsets, _i64p), None,
+                               0, ctypes.byref(total))
+        self._check(rc)
+        ids = np.empty(max(total.value, 1), np.int64)
+        self._check(self._L.vi_search(self._h, _p(queries, _f32p), nq, d, ctypes.c_float(proximity), _p(offsets, _i64p),
+                                      _p(ids, _i64p), total.value, ctypes.byref(total)))
+        return offsets, ids[:total.value]
+
+    def search_verify(self, queries: np.ndarray, proximity: float, distance: float):
+        queries = np.ascontiguousarray(queries, np.float32)
+        if queries.ndim == 1:
+            queries = queries[None, :]
+        nq, d = queries.shape
+        offsets = np.zeros(nq + 1, np.int64)
+        total = ctypes.c_int64(0)
+        self._check(self._L.vi_search_verify(self._h, _p(queries, _f32p), nq, d, ctypes.c_float(proximity),
+                                             ctypes.c_float(distance), _p(offsets, _i64p), None, 0, ctypes.byref(total)))
+        ids = np.empty(max(total.value, 1), np.int64)
+        self._check(self._L.vi_search_verify(self._h, _p(queries, _f32p), nq, d, ctypes.c_float(proximity),
+                                             ctypes.c_float(distance), _p(offsets, _i64p), _p(ids, _i64p), total.value,
+                                             ctypes.byref(total)))
+        return offsets, ids[:total.value]
+
+    def search_device(self, d_queries_ptr: int, nq: int, dims: int, proximity: float, d_offsets_ptr: int,
+                      d_ids_ptr: int, cap: int):
+        total = ctypes.c_int64(0)
+        visits = ctypes.c_int64(0)
+        rc = self._L.vi_search_device(self._h, d_queries_ptr, nq, dims, ctypes.c_float(proximity), d_offsets_ptr,
+                                      d_ids_ptr, cap, ctypes.byref(total), ctypes.byref(visits))
+        self._check(rc)
+        return total.value, visits.value
+
+    def set_collective(self, rank: int, world: int, fn):
+        self._cb = ALLREDUCE_FN(fn) if fn is not None else ALLREDUCE_FN()
+        self._check(self._L.vi_set_collective(self._h, rank, world, self._cb, None))
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.vi_stream(self._h) or 0)
+
+
+# ---- IRangeStore family (host-side staging; children of the split tree live on the device) -------------------------
+class IRangeStore:
+    """VectorIndex/IRangeStore.cs:6-22."""
+
+    def Add(self, id: int, vector) -> None:
+        raise NotImplementedError
+
+    def GetPoints(self) -> Iterator[Tuple[int, np.ndarray]]:
+        raise NotImplementedError
+
+    def Dispose(self) -> None:
+        pass
+
+
+class MemoryRangeStore(IRangeStore):
+    """VectorIndex/MemoryRangeStore.cs:7-32: keeps references to the caller's vectors, insertion order."""
+
+    def __init__(self):
+        self._data = []
+
+    def Add(self, id: int, vector) -> None:
+        self._data.append((int(id), vector))
+
+    def GetPoints(self):
+        return iter(self._data)
+
+
+class FileRangeStore:
+    """VectorIndex/FileRangeStore.cs:10-182: a factory of stores with a fixed dimension count that COPIES what is
+    added.  The reference backs it with a memory-mapped file of (8+4*D)*4*count bytes; the B200 equivalent of that
+    scratch space is the device-resident permutation ping-pong, so this class only validates and stages."""
+
+    def __init__(self, count: int, dimensions: int, buffer: int = 10000):
+        if count < 0 or dimensions <= 0 or dimensions > 32767:
+            raise ValueError("Invalid count or dimensions.")
+        self.count = count
+        self.dimensions = dimensions
+        self.buffer = buffer
+
+    def Dispose(self):
+        pass
+
+    def NextStore(self, rangeId: int, capacity: int) -> IRangeStore:
+        return _FileStore(self, rangeId, capacity)
+
+
+class _FileStore(IRangeStore):
+    def __init__(self, container: FileRangeStore, rangeId: int, capacity: int):
+        self._c = container
+        self._ids = []
+        self._rows = []
+
+    def Add(self, id: int, vector) -> None:
+        v = np.asarray(vector, np.float32)
+        if v.shape[0] != self._c.dimensions:
+            raise ValueError("Invalid length of vector.")  # FileRangeStore.cs:59-64
+        self._ids.append(int(id))
+        self._rows.append(v.copy())
+
+    def GetPoints(self):
+        return iter(zip(self._ids, self._rows))
+
+
+class _RootStore(IRangeStore):
+    """IndexBuilder.cs:200-212: wraps the input; Add is not implemented."""
+
+    def __init__(self, points):
+        self.points = points
+
+    def Add(self, id, vector):
+        raise NotImplementedError()
+
+    def GetPoints(self):
+        return iter(self.points)
+
+
+def _drain(points, batch: int = 65536):
+    """Yields (ids, rows) numpy batches from (ids, rows) arrays or an iterable of (id, vector)."""
+    if isinstance(points, tuple) and len(points) == 2 and isinstance(points[1], np.ndarray) and points[1].ndim == 2:
+        yield np.asarray(points[0], np.int64), points[1]
+        return
+    ids, rows = [], []
+    for id_, v in points:
+        ids.append(int(id_))
+        rows.append(np.asarray(v, np.float32))
+        if len(ids) >= batch:
+            yield np.asarray(ids, np.int64), _stack(rows)
+            ids, rows = [], []
+    if ids:
+        yield np.asarray(ids, np.int64), _stack(rows)
+
+
+def _stack(rows):
+    d = rows[0].shape[0]
+    for r in rows:
+        if r.shape[0] != d:
+            raise ValueError("Invalid length of vector.")
+    return np.stack(rows).astype(np.float32, copy=False)
+
+
+class IndexBuilder:
+    """VectorIndex/IndexBuilder.cs:12-198."""
+
+    @staticmethod
+    def Build(points, storeFactory: Optional[Callable[[int, int], IRangeStore]] = None, *, mode: int = MODE_EXACT,
+              device: int = 0, context: Optional[Context] = None) -> Iterator[Tuple[int, RangeValue]]:
+        """Yields (rangeId, RangeValue) like IndexBuilder.Build (IndexBuilder.cs:23-25, :92).
+
+        `points`: iterable of (id, vector) -- enumerated once -- or a tuple (ids[n], rows[n, d]).
+        `storeFactory(rangeId, capacity)` is accepted for signature compatibility; child ranges never leave the
+        device, so it is not called.  Rows come in breadth-first order (the reference yields depth-first; consumers
+        key by rangeId, Program.cs:18-26)."""
+        ctx = context or Context(device)
+        try:
+            first = True
+            for ids, rows in _drain(points):
+                if first:
+                    ctx.reserve(rows.shape[0], rows.shape[1])
+                    first = False
+                ctx.add(ids, rows)
+            if first:
+                return  # empty input: nothing is yielded (IndexBuilder.cs:70-73)
+            ctx.build(mode)
+            rid, dim, mid, oid = ctx.ranges()
+            for i in range(rid.shape[0]):
+                yield int(rid[i]), RangeValue(int(dim[i]), float(mid[i]), int(oid[i]))
+        finally:
+            if context is None:
+                ctx.close()
+
+
+class VectorIndex:
+    """A built split-tree index resident on one GPU with the Find(vector, distance, predicate) entry shape of
+    MemoryVectorIndex.cs:242-245; traversal semantics are dbo.Search's (DDL.sql:234-295)."""
+
+    def __init__(self, ids: np.ndarray, rows: np.ndarray, *, mode: int = MODE_EXACT, device: int = 0):
+        self.ctx = Context(device)
+        rows = np.ascontiguousarray(rows, np.float32)
+        self.ctx.reserve(rows.shape[0], rows.shape[1])
+        self.ctx.add(ids, rows)
+        self.info = self.ctx.build(mode)
+        self._rows = rows
+        self._ids = np.ascontiguousarray(ids, np.int64)
+        self._by_id = None
+
+    @property
+    def Count(self) -> int:
+        return self.ctx.count
+
+    def Search(self, queries, proximity: float):
+        return self.ctx.search(queries, proximity)
+
+    def Find(self, vector, distance: float, predicate: Optional[Callable[[int, np.ndarray], bool]] = None):
+        """Candidates of the box vector +- distance, each passed to predicate(id, vector) which verifies the match
+        ("predicate should verify the match", MemoryVectorIndex.cs:237-241).  Without a predicate the GPU
+        Euclidean verification kernel is used."""
+        vector = np.asarray(vector, np.float32)
+        if vector.shape[0] != self.ctx.dims:
+            raise ValueError("Invalid vector size.")  # MemoryVectorIndex.cs:254
+        if predicate is None:
+            _, ids = self.ctx.search_verify(vector, distance, distance)
+            yield from (int(i) for i in ids)
+            return
+        _, ids = self.ctx.search(vector, distance)
+        if self._by_id is None:
+            self._by_id = {int(i): k for k, i in enumerate(self._ids)}
+        for i in ids:
+            if predicate(int(i), self._rows[self._by_id[int(i)]]):
+                yield int(i)
+
+    def close(self):
+        self.ctx.close()
