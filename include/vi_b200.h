@@ -40,7 +40,8 @@ enum
 enum
 {
   VI_MODE_EXACT = 0, /* literal float32 sequential Welford, IndexBuilder.cs:175-197: bit-identical range table */
-  VI_MODE_FAST = 1   /* q30: order-independent exact integer sums, HBM-bound, shardable */
+  VI_MODE_FAST = 1   /* qfx: order-independent exact integer sums of 26-bit fixed-point values,
+                        HBM-bound, shardable; Mid within 1e-6 * max|x| of the exact mode's */
 };
 
 typedef struct vi_ctx vi_ctx;
@@ -54,7 +55,7 @@ typedef struct vi_build_info
   int64_t point_visits;  /* sum over levels of points in non-leaf ranges (A_l) */
   int64_t kernel_launches;
   double build_ms;       /* device time of the whole build, CUDA events */
-  int32_t q30_exponent;  /* fast mode: E with max|x| < 2^E */
+  int32_t q_exponent;    /* fast mode: E with max|x| < 2^E */
   int32_t reserved;
 } vi_build_info;
 
@@ -137,6 +138,9 @@ int vi_table_device(const vi_ctx* ctx, const int64_t** range_id, const int32_t**
                     const int64_t** id, const int32_t** low_row, const int32_t** high_row);
 /* CUDA stream (cudaStream_t) all work of this ctx is launched on; for external event timing. */
 void* vi_stream(const vi_ctx* ctx);
+/* Self-test of the exact mode's division-free recurrence step: compares it with IEEE division on `samples`
+ * pseudo-random operand pairs on the device; *mismatches must come back 0. */
+int vi_debug_divcheck(vi_ctx* ctx, uint64_t seed, int64_t samples, int64_t* mismatches);
 
 #ifdef __cplusplus
 }

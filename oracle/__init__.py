@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libvi_oracle.so")
 
 MODE_LITERAL = 0
-MODE_Q30 = 1
+MODE_QFX = 1
 
 _i64p = ctypes.POINTER(ctypes.c_int64)
 _i32p = ctypes.POINTER(ctypes.c_int32)
@@ -49,8 +49,8 @@ def lib() -> ctypes.CDLL:
         L.vio_search_batch.argtypes = [ctypes.c_int64, _i64p, _i32p, _f32p, _i64p, ctypes.c_int32,
                                        ctypes.c_int64, _f32p, ctypes.c_int64, ctypes.c_float, ctypes.c_int64,
                                        _i64p, _i64p, _i64p, _i64p]
-        L.vio_q30_exponent.restype = ctypes.c_int
-        L.vio_q30_exponent.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64]
+        L.vio_qfx_exponent.restype = ctypes.c_int
+        L.vio_qfx_exponent.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64]
         L.vio_distance_l2.restype = ctypes.c_float
         L.vio_distance_l2.argtypes = [_f32p, _f32p, ctypes.c_int32]
         _lib = L
@@ -106,10 +106,10 @@ def build(ids: np.ndarray, rows: np.ndarray, mode: int = MODE_LITERAL) -> RangeT
                       rid[:k].copy())
 
 
-def q30_exponent(rows: np.ndarray) -> int:
+def qfx_exponent(rows: np.ndarray) -> int:
     rows = np.ascontiguousarray(rows, dtype=np.float32)
     n, d = rows.shape
-    return int(lib().vio_q30_exponent(_p(rows, _f32p), n, d, d))
+    return int(lib().vio_qfx_exponent(_p(rows, _f32p), n, d, d))
 
 
 def search(table: RangeTable, queries: np.ndarray, proximity: float):

@@ -76,8 +76,8 @@ def build_literal(ids, rows):
     return out
 
 
-def build_q30(ids, rows):
-    """The fast-mode specification: exact integer sums of xi = rint(x * 2^(30-E))."""
+def build_qfx(ids, rows):
+    """The fast-mode specification: exact integer sums of xi = rint(x * 2^(26-E))."""
     rows = np.asarray(rows, np.float32)
     ids = [int(i) for i in ids]
     finite = np.abs(rows[np.isfinite(rows)])
@@ -90,7 +90,7 @@ def build_q30(ids, rows):
     else:
         e = 0
     e = min(max(e, -96), 128)
-    k = np.float32(2.0) ** np.float32(30 - e)
+    k = np.float32(2.0) ** np.float32(26 - e)
     with np.errstate(all="ignore"):
         y = rows * k
     y = np.where(np.isnan(y), np.float32(0), y)
@@ -131,7 +131,7 @@ def build_q30(ids, rows):
             for i in range(1, len(keys)):
                 if (keys[i] > keys[index]) if mx else (keys[i] < keys[index]):
                     index = i
-            mid = np.float32((np.float64(s1[index]) / np.float64(n)) * np.float64(2.0) ** (e - 30))
+            mid = np.float32((np.float64(s1[index]) / np.float64(n)) * np.float64(2.0) ** (e - 26))
         pivot = _trunc_div(idn, n)
         out.append((range_id, index, mid, pivot))
         lo, hi = [], []

@@ -26,7 +26,7 @@
  *
  * Two build modes:
  *   mode 0  "literal": the reference's arithmetic, bit for bit.
- *   mode 1  "q30":     the B200 fast mode's *specification* (order-independent fixed-point integer sums),
+ *   mode 1  "qfx":     the B200 fast mode's *specification* (order-independent fixed-point integer sums),
  *                      restated on the CPU so the GPU fast path can be checked bit-exactly against it.  It is
  *                      not the reference's arithmetic; tests report its divergence from mode 0.
  */
@@ -44,8 +44,9 @@ typedef unsigned __int128 u128;
 #define VIO_ERR_NOMEM -3
 #define VIO_ERR_ARG -4
 
-/* q30 mode: a range is "resolved" when some dimension has n^2 * var >= n^2 * 2^(2*10) in quantised units */
-#define VIO_Q30_MIN_RES_BITS 10
+/* qfx mode: a range is "resolved" when some dimension has n^2 * var >= n^2 * 2^(2*10) in quantised units */
+#define VIO_QFX_MIN_RES_BITS 10
+#define VIO_QBITS 26 /* fixed-point fraction bits: xi = rint(x * 2^(VIO_QBITS - E)), |xi| <= 2^26 */
 
 /* float.CompareTo as used by Comparer<float>.Default inside Enumerable.MaxBy (IndexBuilder.cs:77-79):
  * NaN sorts below every number, NaN == NaN, -0 == +0. */
@@ -86,8 +87,8 @@ static int push(work_stack* s, work_item it)
   return 1;
 }
 
-/* Quantisation exponent of the q30 mode: smallest E (clamped) with max|x| < 2^E, from frexp. */
-int vio_q30_exponent(const float* rows, int64_t n, int32_t d, int64_t ld)
+/* Quantisation exponent of the qfx mode: smallest E (clamped) with max|x| < 2^E, from frexp. */
+int vio_qfx_exponent(const float* rows, int64_t n, int32_t d, int64_t ld)
 {
   float amax = 0.0f;
   for (int64_t r = 0; r < n; ++r)
@@ -104,7 +105,7 @@ int vio_q30_exponent(const float* rows, int64_t n, int32_t d, int64_t ld)
   return e;
 }
 
-static inline int32_t q30_quantise(float x, float k)
+static inline int32_t qfx_quantise(float x, float k)
 {
   /* GPU: __float2int_rn(x * k) : round-to-nearest-even, NaN -> 0, saturating. */
   float y = x * k;
@@ -116,7 +117,7 @@ static inline int32_t q30_quantise(float x, float k)
 
 /*
  * Build the range table.
- *   ids[n], rows[n*ld] (row r at rows + r*ld, d used floats), mode 0 literal / 1 q30.
+ *   ids[n], rows[n*ld] (row r at rows + r*ld, d used floats), mode 0 literal / 1 qfx.
  * Output rows are written in the reference's emission order (DFS, high child popped first:
  * IndexBuilder.cs:128-129 pushes low then high onto a Stack).  Returns VIO_OK and *out_count.
  */
@@ -144,9 +145,9 @@ int vio_build(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float*
   double qinv = 1.0;
   if (mode == 1)
   {
-    qe = vio_q30_exponent(rows, n, d, ld);
-    qk = ldexpf(1.0f, 30 - qe);
-    qinv = ldexp(1.0, qe - 30);
+    qe = vio_qfx_exponent(rows, n, d, ld);
+    qk = ldexpf(1.0f, VIO_QBITS - qe);
+    qinv = ldexp(1.0, qe - VIO_QBITS);
   }
 
   work_item root = {0, 0, n, 1}; /* IndexBuilder.cs:33 */
@@ -167,14 +168,14 @@ int vio_build(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float*
     int literal = (mode == 0);
     if (mode == 1)
     {
-      /* q30 specification (DESIGN.md "fast mode"): exact integer sums of xi = rint(x * 2^(30-E)). */
+      /* qfx specification (DESIGN.md "fast mode"): exact integer sums of xi = rint(x * 2^(26-E)). */
       for (int32_t i = 0; i < d; ++i) { s1[i] = 0; s2[i] = 0; }
       for (int64_t j = 0; j < count; ++j)
       {
         const float* v = rows + p[j] * ld;
         for (int32_t i = 0; i < d; ++i)
         {
-          int64_t xi = q30_quantise(v[i], qk);
+          int64_t xi = qfx_quantise(v[i], qk);
           s1[i] += xi;
           s2[i] += (u128)(uint64_t)(xi * xi);
         }
@@ -182,7 +183,7 @@ int vio_build(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float*
       }
       /* key K = n*S2 - S1^2 (exact, >= 0); even depth argmax, odd depth argmin, lowest index wins ties */
       u128 bestk = 0;
-      u128 thr = ((u128)(uint64_t)count * (u128)(uint64_t)count) << (2 * VIO_Q30_MIN_RES_BITS);
+      u128 thr = ((u128)(uint64_t)count * (u128)(uint64_t)count) << (2 * VIO_QFX_MIN_RES_BITS);
       int resolved = 0;
       for (int32_t i = 0; i < d; ++i)
       {

@@ -1,5 +1,5 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
-Bit-exact for both modes: exact mode vs the literal oracle, fast mode vs the q30 specification oracle."""
+Bit-exact for both modes: exact mode vs the literal oracle, fast mode vs the qfx specification oracle."""
 import numpy as np
 import pytest
 
@@ -74,7 +74,7 @@ def test_wide_rows_768(mode):
 
 @pytest.mark.parametrize("mode", MODES)
 def test_one_hot_crafted_set(mode):
-    # Program.cs:54-66; literal mode must pick dimension 3 at the root, q30 dimension 0
+    # Program.cs:54-66; literal mode must pick dimension 3 at the root, qfx dimension 0
     ids, rows = ds.one_hot(1536)
     rid, dim, mid, oid, _ = gpu_table(ids, rows, mode)
     assert dim[0] == (3 if mode == vi.MODE_EXACT else 0)
@@ -226,3 +226,22 @@ def test_textindex_rows():
             assert lo[k] in (-1, 2 * rid[k] + 1) and hi[k] in (-1, 2 * rid[k] + 2)
             assert (lo[k] == -1) == (2 * rid[k] + 1 not in have)
             assert (hi[k] == -1) == (2 * rid[k] + 2 not in have)
+
+
+def test_fast_division_is_correctly_rounded():
+    # exact mode replaces (value - pa) / count by a reciprocal + two Markstein corrections (vi_stats_exact.cuh);
+    # the device self-test compares it with IEEE division on 2e9 operand pairs
+    with vi.Context(0) as ctx:
+        assert ctx.divcheck(12345, 2_000_000_000) == 0
+        assert ctx.divcheck(987654321, 500_000_000) == 0
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_mid_size_ranges_all_classes(mode):
+    # 40k x 96: exercises chunked (>= 4096), warp-per-range and team-per-range classes of the fast mode
+    ids, rows = ds.uniform(40_000, 96, seed=21)
+    assert_same_table(ids, rows, mode)
+    ids, rows = ds.unit_gaussian(9000, 128, seed=22)   # FULL <8,4> shape
+    assert_same_table(ids, rows, mode)
+    ids, rows = ds.unit_gaussian(5000, 100, seed=23)   # padded row width, guarded columns
+    assert_same_table(ids, rows, mode)

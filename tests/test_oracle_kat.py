@@ -12,19 +12,19 @@ def _tbl(ids, rows, mode=oracle.MODE_LITERAL):
     return oracle.build(np.asarray(ids, np.int64), np.asarray(rows, np.float32), mode)
 
 
-@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_QFX])
 def test_empty(mode):
     t = _tbl(np.zeros(0, np.int64), np.zeros((0, 4), np.float32), mode)
     assert len(t) == 0  # IndexBuilder.cs:70-73
 
 
-@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_QFX])
 def test_single_point(mode):
     t = _tbl([42], [[0.5, -0.25, 3.0]], mode)
     assert t.as_dict() == {0: (-1, 0.0, 42)}  # IndexBuilder.cs:81-82
 
 
-@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_QFX])
 def test_two_points_one_dim_differs(mode):
     # even depth => max variance => dim 1; mean 0.5; ids 7, 9 -> pivot trunc(16/2) = 8
     t = _tbl([7, 9], [[1.0, 1.0, 1.0], [1.0, 0.0, 1.0]], mode).as_dict()
@@ -34,7 +34,7 @@ def test_two_points_one_dim_differs(mode):
     assert len(t) == 3
 
 
-@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_QFX])
 def test_identical_vectors_split_by_id(mode):
     # IndexBuilder.cs:115 tie-break: value == Mid and id > Id -> high.  Id = trunc(13 / 2) = 6
     t = _tbl([3, 10], [[0.25, 0.25], [0.25, 0.25]], mode).as_dict()
@@ -43,7 +43,7 @@ def test_identical_vectors_split_by_id(mode):
     assert t[2] == (-1, 0.0, 10)
 
 
-@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_QFX])
 def test_negative_ids_truncate_toward_zero(mode):
     # Int128 division truncates toward zero (IndexBuilder.cs:87): (-3 + -6) / 2 = -4 (floor would give -5)
     t = _tbl([-3, -6], [[0.5], [0.5]], mode).as_dict()
@@ -52,7 +52,7 @@ def test_negative_ids_truncate_toward_zero(mode):
     assert t[2] == (-1, 0.0, -3)
 
 
-@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_QFX])
 def test_inseparable_points_overflow_at_depth_62(mode):
     # ids {-4,-5}: pivot trunc(-9/2) = -4; neither id is > -4, both go low forever (a floor division would
     # have separated them).  The reference dies with OverflowException from checked(rangeId*2+1)
@@ -61,7 +61,7 @@ def test_inseparable_points_overflow_at_depth_62(mode):
         _tbl([-4, -5], [[0.5], [0.5]], mode)
 
 
-@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_QFX])
 def test_min_variance_on_odd_depth(mode):
     # 4 points, dim0 spread wide, dim1 constant, dim2 small spread.
     rows = np.array([[-1.0, 0.5, 0.01], [-0.9, 0.5, -0.01], [0.9, 0.5, 0.02], [1.0, 0.5, -0.02]], np.float32)
@@ -74,15 +74,15 @@ def test_min_variance_on_odd_depth(mode):
     assert t[5] == (-1, 0.0, 2) and t[6] == (-1, 0.0, 3)
 
 
-def test_one_hot_sentinel_literal_vs_q30():
+def test_one_hot_sentinel_literal_vs_qfx():
     # Program.cs:54-66 crafted set.  All dimensions tie mathematically; literal float32 Welford breaks the tie
     # by rounding noise and picks dimension 3 (hard part 1); exact integer sums pick dimension 0.
     ids, rows = datasets.one_hot(1536)
     lit = _tbl(ids, rows, oracle.MODE_LITERAL)
-    q30 = _tbl(ids, rows, oracle.MODE_Q30)
+    qfx = _tbl(ids, rows, oracle.MODE_QFX)
     assert lit.dimension[0] == 3
-    assert q30.dimension[0] == 0
-    for t in (lit, q30):
+    assert qfx.dimension[0] == 0
+    for t in (lit, qfx):
         assert (t.dimension == -1).sum() == 1536
         assert sorted(t.id[t.dimension == -1].tolist()) == list(range(1536))
 
@@ -99,7 +99,7 @@ def _check_invariants(t, ids):
     assert len(t) == 2 * len(ids) - 1  # no empty child for distinct-id, finite data
 
 
-@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_Q30])
+@pytest.mark.parametrize("mode", [oracle.MODE_LITERAL, oracle.MODE_QFX])
 def test_structural_invariants(mode):
     ids, rows = datasets.uniform(3000, 24, seed=5)
     ids = ids * 3 + 11
@@ -130,11 +130,11 @@ def test_c_oracle_matches_numpy_restatement_literal(n, d, seed):
 
 
 @pytest.mark.parametrize("n,d,seed,scale", [(2, 5, 1, 1.0), (33, 3, 2, 1000.0), (300, 16, 3, 1e-3), (400, 96, 4, 1.0)])
-def test_c_oracle_matches_numpy_restatement_q30(n, d, seed, scale):
+def test_c_oracle_matches_numpy_restatement_qfx(n, d, seed, scale):
     ids, rows = datasets.uniform(n, d, seed)
     rows = (rows * np.float32(scale)).astype(np.float32)
-    t = _tbl(ids, rows, oracle.MODE_Q30)
-    ref = np_oracle.build_q30(ids, rows)
+    t = _tbl(ids, rows, oracle.MODE_QFX)
+    ref = np_oracle.build_qfx(ids, rows)
     d_ref = {r[0]: (r[1], float(r[2]), r[3]) for r in ref}
     got = t.as_dict()
     assert got.keys() == d_ref.keys()
@@ -150,7 +150,7 @@ def test_duplicates_and_constant_columns():
     rows = np.concatenate([base, base, base], 0)
     rows[:, 2] = 0.125
     ids = np.arange(150, dtype=np.int64)[::-1].copy()
-    for mode in (oracle.MODE_LITERAL, oracle.MODE_Q30):
+    for mode in (oracle.MODE_LITERAL, oracle.MODE_QFX):
         _check_invariants(_tbl(ids, rows, mode), ids)
 
 

@@ -362,4 +362,11 @@ int vi_table_device(const vi_ctx* ctx, const int64_t** range_id, const int32_t**
 
 void* vi_stream(const vi_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+int vi_debug_divcheck(vi_ctx* ctx, uint64_t seed, int64_t samples, int64_t* mismatches)
+{
+  if (!ctx || !mismatches || samples < 0) return VI_ERR_INVALID_ARG;
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  return vi_debug_divcheck_impl(ctx, seed, samples, mismatches);
+}
+
 }  // extern "C"

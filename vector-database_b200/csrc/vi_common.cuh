@@ -14,9 +14,9 @@ typedef int64_t i64;
 typedef __int128 i128;
 typedef unsigned __int128 u128;
 
-// Ranges with at least this many points are "big": their statistics are computed by many CTAs (fast mode) or
-// by one thread per (range, dimension) chain (exact mode); smaller ranges are owned by one team/warp.
-constexpr u32 VI_BIG = 512;
+// Ranges with at least t_big points are "big": their statistics are computed by many CTAs (fast mode) or by one
+// thread per (range, dimension) chain (exact mode); smaller ranges are owned by one team/warp (vi_build.cu).
+constexpr u32 VI_MIN_BIG = 512;  // smallest allowed "big range" threshold (sizes the big-range work space)
 // Rows of a big range handled by one CTA of the fast-mode statistics kernel.
 constexpr u32 VI_CHUNK = 4096;
 constexpr int VI_NUM_SMS = 148;
@@ -48,7 +48,9 @@ struct LevelTotals  // pinned host, written by the device at the end of every le
   u32 pos;       // next-level active positions
   u32 nbig;      // next-level big segments
   u32 chunks;    // next-level fast-mode chunk count
-  u32 pad[3];
+  u32 err;       // range table capacity exceeded
+  u32 minseg;    // smallest / largest next-level range
+  u32 maxseg;
 };
 
 struct vi_ctx
@@ -165,6 +167,7 @@ __device__ __forceinline__ u32 hi_before(const u32* __restrict__ wpre, const u32
 }
 
 // build entry points implemented in vi_build.cu / vi_search.cu
+int vi_debug_divcheck_impl(vi_ctx* ctx, uint64_t seed, int64_t samples, int64_t* mismatches);
 int vi_build_impl(vi_ctx* ctx, int mode);
 int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proximity, i64* d_offsets, i64* d_ids,
                    int64_t cap, int64_t* total, int64_t* visits, bool have_offsets);

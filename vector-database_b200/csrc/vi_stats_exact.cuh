@@ -1,0 +1,283 @@
+// vi_stats_exact.cuh -- exact-mode statistics: the literal float32 recurrence of IndexBuilder.cs:159-197, one chain
+// per (range, dimension) in stable position order, so the range table is bit-identical to the reference's.
+//
+// The recurrence is a serial dependency (mean_k depends on mean_{k-1}); its latency per point is what bounds the
+// top levels.  The divide (value - pa) / count dominates that latency, so it is taken off the critical path:
+// count is known in advance, r = RN(1/count) is computed by another lane ahead of time, and the quotient is
+// q0 = d*r followed by two Markstein corrections q <- fma(fma(-q, c, d), r, q).  With r correctly rounded the first
+// correction makes q faithful and the second makes it RN(d/c) (Markstein 1990; Muller et al., Handbook of
+// Floating-Point Arithmetic, ch. 4) provided d - q*c is exact, which holds for 2^-100 <= |d| <= 2^100 and
+// 1 <= c <= 2^31; anything else (zero, tiny, huge, Inf, NaN) takes __fdiv_rn.  vi_debug_divcheck compares the two
+// on the device (tests/test_gpu_parity.py::test_fast_division_is_correctly_rounded).
+//
+//   n <  t_big   one warp per range, a lane runs CHX chains (dims lane, lane+32, ...)   k_stats_small_exact
+//   n >= t_big   one warp per (range, 32 dims): one chain per thread, 2 x 32 rows of register prefetch
+//                (k_stats_big_exact) + k_finalize_big_exact for the arg-max and the id sum
+#pragma once
+#include "vi_stats_common.cuh"
+
+// RN(d / c) for 2^-100 <= |d| <= 2^100 or d == +-0 (the quotient of a zero keeps the zero's sign since c > 0)
+__device__ __forceinline__ float div_core(float d, float c, float r)
+{
+  const float q0 = __fmul_rn(d, r);
+  const float e0 = __fmaf_rn(-q0, c, d);
+  const float q1 = __fmaf_rn(e0, r, q0);
+  const float e1 = __fmaf_rn(-q1, c, d);
+  const float q2 = __fmaf_rn(e1, r, q1);
+  return d == 0.f ? d : q2;
+}
+
+// operands div_core does not cover: tiny non-zero, huge, Inf, NaN
+__device__ __forceinline__ bool div_needs_ieee(float d)
+{
+  const float ad = fabsf(d);
+  return !(ad <= 0x1p100f) || (ad < 0x1p-100f && ad != 0.f);
+}
+
+__device__ __forceinline__ float div_by_count(float d, float c, float r)
+{
+  return div_needs_ieee(d) ? __fdiv_rn(d, c) : div_core(d, c, r);
+}
+
+// same results as welford_step (vi_stats_common.cuh), with r = RN(1/c) supplied
+__device__ __forceinline__ void welford_step_r(float& mean, float& q, float value, float c, float r)
+{
+  const float d1 = __fsub_rn(value, mean);
+  const float a = __fadd_rn(mean, div_by_count(d1, c, r));
+  q = __fadd_rn(q, __fmul_rn(d1, __fsub_rn(value, a)));
+  mean = a;
+}
+
+// branch-free speculative step: valid unless `bad` comes back set, in which case the caller redoes the steps
+// with welford_step_r from its saved state
+__device__ __forceinline__ void welford_step_spec(float& mean, float& q, float value, float c, float r, bool& bad)
+{
+  const float d1 = __fsub_rn(value, mean);
+  bad |= div_needs_ieee(d1);
+  const float a = __fadd_rn(mean, div_core(d1, c, r));
+  q = __fadd_rn(q, __fmul_rn(d1, __fsub_rn(value, a)));
+  mean = a;
+}
+
+__device__ __forceinline__ ExBest ex_reduce(ExBest b) { return ex_reduce_w<32>(b, 0xffffffffu); }
+
+template <int CHX>
+__global__ void __launch_bounds__(256)
+k_stats_small_exact(SegLevel sg, u32 R, u32 nmax, const u32* __restrict__ perm, const i64* __restrict__ pid,
+                    const float* __restrict__ rows, int ld, int dims, int mx, StatsOut out)
+{
+  const u32 s = (blockIdx.x * 256u + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= R) return;
+  const u32 n = sg.count[s];
+  if (n >= nmax) return;
+  const u32 S = sg.start[s];
+  const u32* pp = perm + S;
+  ExBest best;
+  best.key = 0.f;
+  best.mean = 0.f;
+  best.idx = 0x7fffffff;
+  for (int c0 = 0; c0 < dims; c0 += 32 * CHX)
+  {
+    float mean[CHX], q[CHX];
+    {
+      const float* rp = rows + (size_t)pp[0] * ld;
+#pragma unroll
+      for (int k = 0; k < CHX; ++k)
+      {
+        const int c = c0 + k * 32 + lane;
+        mean[k] = (c < dims) ? ldg_f_stream(rp + c) : 0.f;  // InitStats, IndexBuilder.cs:159-173
+        q[k] = 0.f;
+      }
+    }
+    u32 mine = (lane < n) ? pp[lane] : 0u;
+    for (u32 jb = 0; jb < n; jb += 32)
+    {
+      const u32 nxt = (jb + 32 + lane < n) ? pp[jb + 32 + lane] : 0u;
+      const u32 m = min(32u, n - jb);
+      const float cmine = (float)(jb + lane + 1u);  // (float)(Count + 1), IndexBuilder.cs:185-186
+      const float rmine = __frcp_rn(cmine);
+#pragma unroll 4
+      for (u32 jj = (jb == 0 ? 1u : 0u); jj < m; ++jj)
+      {
+        const u32 r = __shfl_sync(0xffffffffu, mine, jj);
+        const float cnt = __shfl_sync(0xffffffffu, cmine, jj);
+        const float rc = __shfl_sync(0xffffffffu, rmine, jj);
+        const float* rp = rows + (size_t)r * ld;
+        float v[CHX];
+#pragma unroll
+        for (int k = 0; k < CHX; ++k)
+        {
+          const int c = c0 + k * 32 + lane;
+          v[k] = (c < dims) ? ldg_f_stream(rp + c) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < CHX; ++k) welford_step_r(mean[k], q[k], v[k], cnt, rc);
+      }
+      mine = nxt;
+    }
+#pragma unroll
+    for (int k = 0; k < CHX; ++k)
+    {
+      const int d = c0 + k * 32 + lane;
+      if (d < dims)
+      {
+        const float key = mx ? q[k] : -q[k];  // IndexBuilder.cs:79
+        if (ex_better(key, d, best.key, best.idx))
+        {
+          best.key = key;
+          best.mean = mean[k];
+          best.idx = d;
+        }
+      }
+    }
+  }
+  best = ex_reduce(best);
+  const i64 pivot = range_mean_id<32>(pid + S, n, lane, 0xffffffffu);
+  if (lane == 0) write_split(sg, out, s, best.idx, best.mean, pivot);
+}
+
+constexpr int EXU = 32;   // rows per prefetch group
+constexpr int EXNG = 4;   // groups in flight (128 rows ahead of the recurrence)
+
+__global__ void __launch_bounds__(32)
+k_stats_big_exact(SegLevel sg, const u32* __restrict__ big_list, u32 nblk, const u32* __restrict__ perm,
+                  const float* __restrict__ rows, int ld, int dims, float2* __restrict__ gstats)
+{
+  const u32 slot = blockIdx.x / nblk;
+  const int col = (int)(blockIdx.x % nblk) * 32 + threadIdx.x;
+  const int lane = threadIdx.x;
+  const u32 s = big_list[slot];
+  const u32 S = sg.start[s], n = sg.count[s];
+  const bool act = col < dims;
+  const float* base = rows + (act ? col : 0);
+  const u32* pp = perm + S;
+
+  // Rows are prefetched with cp.async into a per-warp shared-memory ring (EXNG groups of EXU rows, a lane copies
+  // and later reads back only its own 4 bytes, so no barrier is needed).  Register prefetch would not do: a warp
+  // has 6 scoreboard slots, and waiting for the oldest of 64 outstanding loads also waits for the youngest.
+  __shared__ float ring[EXNG][EXU][32];
+  float mean = ldg_f_stream(base + (size_t)pp[0] * ld), q = 0.f;
+  auto load_perm = [&](u32 g) -> u32
+  {
+    const u32 j = 1u + g * EXU + lane;
+    return (j < n) ? pp[j] : 0u;
+  };
+  auto issue = [&](u32 g, u32 pv)  // group g = rows 1 + g*EXU .. ; always commits (uniform group counting)
+  {
+    const u32 j0 = 1u + g * EXU;
+    const u32 dst = (u32)__cvta_generic_to_shared(&ring[g % EXNG][0][lane]);
+#pragma unroll
+    for (int u = 0; u < EXU; ++u)
+    {
+      const u32 r = __shfl_sync(0xffffffffu, pv, u);
+      if (j0 + u < n)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + u * 128), "l"(base + (size_t)r * ld) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const u32 ngroups = (n - 1 + EXU - 1) / EXU;
+#pragma unroll
+  for (int g = 0; g < EXNG; ++g) issue(g, load_perm(g));
+  u32 pnext = load_perm(EXNG);
+  for (u32 g = 0; g < ngroups; ++g)
+  {
+    asm volatile("cp.async.wait_group %0;" ::"n"(EXNG - 1) : "memory");
+    float v[EXU];
+#pragma unroll
+    for (int u = 0; u < EXU; ++u) v[u] = ring[g % EXNG][u][lane];
+    issue(g + EXNG, pnext);  // refill the slot just drained
+    pnext = load_perm(g + EXNG + 1);
+    const u32 j0 = 1u + g * EXU;
+    const float cmine = (float)(j0 + lane + 1u);  // (float)(Count + 1), IndexBuilder.cs:185-186
+    const float rmine = __frcp_rn(cmine);
+    float cn[EXU], rc[EXU];
+#pragma unroll
+    for (int u = 0; u < EXU; ++u)
+    {
+      cn[u] = __shfl_sync(0xffffffffu, cmine, u);
+      rc[u] = __shfl_sync(0xffffffffu, rmine, u);
+    }
+    if (j0 + EXU <= n)
+    {
+      // full group: 32 branch-free steps; redo with IEEE division only if an operand was out of div_core's range
+      const float m0 = mean, q0 = q;
+      bool bad = false;
+#pragma unroll
+      for (int u = 0; u < EXU; ++u) welford_step_spec(mean, q, v[u], cn[u], rc[u], bad);
+      if (bad)
+      {
+        mean = m0;
+        q = q0;
+#pragma unroll  // (static indexes keep v/cn/rc in registers)
+        for (int u = 0; u < EXU; ++u) welford_step_r(mean, q, v[u], cn[u], rc[u]);
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int u = 0; u < EXU; ++u)
+        if (j0 + u < n) welford_step_r(mean, q, v[u], cn[u], rc[u]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (act) gstats[(size_t)slot * dims + col] = make_float2(mean, q);
+}
+
+__global__ void __launch_bounds__(256)
+k_finalize_big_exact(SegLevel sg, const u32* __restrict__ big_list, u32 nbig, const float2* __restrict__ gstats,
+                     const i64* __restrict__ pid, int dims, int mx, StatsOut out)
+{
+  const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nbig) return;
+  const u32 s = big_list[warp];
+  const u32 S = sg.start[s], n = sg.count[s];
+  ExBest best;
+  best.key = 0.f;
+  best.mean = 0.f;
+  best.idx = 0x7fffffff;
+  for (int d = lane; d < dims; d += 32)
+  {
+    const float2 st = gstats[(size_t)warp * dims + d];
+    const float key = mx ? st.y : -st.y;
+    if (ex_better(key, d, best.key, best.idx))
+    {
+      best.key = key;
+      best.mean = st.x;
+      best.idx = d;
+    }
+  }
+  best = ex_reduce(best);
+  const i64 pivot = range_mean_id<32>(pid + S, n, lane, 0xffffffffu);
+  if (lane == 0) write_split(sg, out, s, best.idx, best.mean, pivot);
+}
+
+// debug: compares div_by_count with __fdiv_rn on pseudo-random operands; returns the mismatch count
+__global__ void k_divcheck(u64 seed, u64 per_thread, unsigned long long* mismatches)
+{
+  u64 x = seed ^ ((u64)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull);
+  unsigned long long bad = 0;
+  for (u64 i = 0; i < per_thread; ++i)
+  {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
+    const u32 cbits = (u32)(x >> 40);          // 24-bit counts, plus some larger ones
+    u32 ci = (i & 7) == 0 ? (u32)(x >> 33) : cbits;
+    if (ci < 2) ci = 2;
+    const float c = (float)ci;
+    float d;
+    switch ((x >> 8) & 3)
+    {
+      case 0: d = __uint_as_float((u32)x); break;                                   // any bit pattern
+      case 1: d = __uint_as_float(((u32)x & 0x807fffffu) | (((u32)(x >> 32) % 60 + 97) << 23)); break;  // 2^-30..2^29
+      case 2: d = __uint_as_float(((u32)x & 0x807fffffu) | (((u32)(x >> 32) % 16 + 120) << 23)); break; // near 1
+      default: d = (float)(int)(x >> 20) * 0x1p-20f; break;
+    }
+    if ((i & 1023) == 5) d = 0.f;
+    if ((i & 1023) == 6) d = -0.f;
+    const float a = div_by_count(d, c, __frcp_rn(c));
+    const float b = __fdiv_rn(d, c);
+    if (__float_as_uint(a) != __float_as_uint(b) && !(isnan(a) && isnan(b))) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}

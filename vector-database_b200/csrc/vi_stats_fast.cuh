@@ -1,0 +1,408 @@
+// vi_stats_fast.cuh -- fast-mode statistics + split choice (replaces IndexBuilder.cs:55-88 for every open range).
+//
+// qfx (fixed point): every component is quantised once, xi = rint(x * 2^(QBITS-E)) with max|x| < 2^E and
+// QBITS = 26, and the per-(range, dim) sums S1 = sum xi and S2 = sum xi^2 are EXACT integers, so any reduction
+// order -- lanes, teams, CTAs, atomics, GPUs -- gives the same bits.  Split choice: K = n*S2 - S1^2 (exact,
+// 128 bits), arg-max on even depths and arg-min on odd depths, lowest index on ties;
+// Mid = float((double)S1 / n * 2^(E-QBITS)).  A range in which no dimension has K >= n^2 * 2^20 (stdev below 2^10
+// quantisation steps) takes the reference's float32 statistics instead (welford_team).  The CPU statement of the
+// same rules is oracle/vi_oracle.c mode 1.
+//
+// |xi| <= 2^26, xi^2 <= 2^52: a lane that accumulates fewer than 4096 rows keeps S1 and S2 in one 64-bit register
+// pair each, so an element costs FMUL + F2I + 2 x IMAD.WIDE.  Wider totals only appear where partial sums meet
+// (shared/global integer atomics on 32-bit limbs, k_finalize_big_fast).
+//
+// Work decomposition by range size n (the host launches only the classes present on a level):
+//   n <  t_team           one TEAM of TS lanes per range   (k_stats_small_fast<TS,CH,FULL,false>)
+//   t_team <= n < t_big   one WARP per range, its 32/TS teams stride the rows (k_stats_small_fast<..,true>)
+//   n >= t_big            VI_CHUNK-row chunks, one CTA each, integer atomics into gacc (k_stats_big_fast) +
+//                         one warp per range for the arg-max (k_finalize_big_fast);   t_big <= 4096
+// A lane owns CH float4 column chunks of a row: 16-byte loads, a team reads one whole row per step.
+// FULL: the row is exactly TS*CH float4 wide (no column guards, one pass): D = 96 -> <8,3>, D = 768 -> <32,6>.
+#pragma once
+#include "vi_stats_common.cuh"
+
+constexpr int VI_QBITS = 26;
+constexpr u32 VI_MAX_ROWS_PER_LANE = 1u << (64 - 2 * VI_QBITS);  // 4096
+
+__device__ __forceinline__ void qfx_acc(i64& s1, u64& s2, float x, float k)
+{
+  const int xi = __float2int_rn(__fmul_rn(x, k));
+  // mad.wide.s32: 32x32 -> 64-bit product added to a 64-bit accumulator in one instruction
+  asm("mad.wide.s32 %0, %1, 1, %0;" : "+l"(s1) : "r"(xi));
+  asm("mad.wide.s32 %0, %1, %1, %0;" : "+l"(s2) : "r"(xi));
+}
+
+__device__ __forceinline__ void qfx_acc4(i64* s1, u64* s2, const float4& x, float k)
+{
+  qfx_acc(s1[0], s2[0], x.x, k);
+  qfx_acc(s1[1], s2[1], x.y, k);
+  qfx_acc(s1[2], s2[2], x.z, k);
+  qfx_acc(s1[3], s2[3], x.w, k);
+}
+
+struct Key128
+{
+  u64 hi, lo;
+};
+
+__device__ __forceinline__ bool key_lt(const Key128& a, const Key128& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+__device__ __forceinline__ bool key_eq(const Key128& a, const Key128& b) { return a.hi == b.hi && a.lo == b.lo; }
+
+// K = n*S2 - S1^2 >= 0 (Cauchy-Schwarz), exact: n < 2^32, S2 = s2hi:s2lo < 2^96, |S1| < 2^63
+__device__ __forceinline__ Key128 qfx_key(u32 n, i64 s1, u64 s2lo, u64 s2hi)
+{
+  const u64 plo = (u64)n * s2lo;
+  const u64 phi = __umul64hi((u64)n, s2lo) + (u64)n * s2hi;
+  const u64 a = s1 < 0 ? (u64)(-s1) : (u64)s1;
+  const u64 qlo = a * a, qhi = __umul64hi(a, a);
+  Key128 k;
+  k.lo = plo - qlo;
+  k.hi = phi - qhi - (plo < qlo ? 1ull : 0ull);
+  return k;
+}
+
+// n^2 * 2^(2*VI_QFX_MIN_RES_BITS)
+constexpr int VI_QFX_MIN_RES_BITS = 10;
+__device__ __forceinline__ Key128 qfx_threshold(u32 n)
+{
+  const u64 n2 = (u64)n * (u64)n;
+  Key128 t;
+  t.lo = n2 << (2 * VI_QFX_MIN_RES_BITS);
+  t.hi = n2 >> (64 - 2 * VI_QFX_MIN_RES_BITS);
+  return t;
+}
+
+struct QfxBest
+{
+  Key128 key;
+  i64 s1;
+  int idx;  // INT_MAX = none
+};
+
+__device__ __forceinline__ bool qfx_better(bool mx, const Key128& k, int i, const Key128& bk, int bi)
+{
+  if (i == 0x7fffffff) return false;
+  if (bi == 0x7fffffff) return true;
+  if (!key_eq(k, bk)) return mx ? key_lt(bk, k) : key_lt(k, bk);
+  return i < bi;  // lowest index wins ties (MaxBy keeps the first maximum, IndexBuilder.cs:77-79)
+}
+
+template <int W>
+__device__ __forceinline__ QfxBest qfx_reduce(QfxBest b, bool mx, u32 mask)
+{
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1)
+  {
+    QfxBest t;
+    t.key.hi = __shfl_xor_sync(mask, b.key.hi, o);
+    t.key.lo = __shfl_xor_sync(mask, b.key.lo, o);
+    t.s1 = __shfl_xor_sync(mask, b.s1, o);
+    t.idx = __shfl_xor_sync(mask, b.idx, o);
+    if (qfx_better(mx, t.key, t.idx, b.key, b.idx)) b = t;
+  }
+  return b;
+}
+
+__device__ __forceinline__ float qfx_mid(i64 s1, u32 n, double qinv)
+{
+  return __double2float_rn(__dmul_rn(__ddiv_rn(__ll2double_rn(s1), (double)n), qinv));
+}
+
+template <int TS, int CH, bool FULL, bool WPS>
+__global__ void __launch_bounds__(256, (TS * CH <= 32) ? 3 : 1)
+k_stats_small_fast(SegLevel sg, u32 R, u32 nmin, u32 nmax, const u32* __restrict__ perm, const i64* __restrict__ pid,
+                   const float* __restrict__ rows, int ld, int dims, float qk, double qinv, int mx, StatsOut out)
+{
+  constexpr int NTW = 32 / TS;            // teams per warp
+  constexpr int TPS = WPS ? NTW : 1;      // teams sharing one range
+  constexpr int GS = WPS ? 32 : TS;       // lanes sharing one range
+  const int lane = threadIdx.x & 31;
+  const int tl = lane % TS;               // lane inside its team
+  const int trow = WPS ? lane / TS : 0;   // first row (of every TPS) this team takes
+  const int gl = WPS ? lane : tl;         // lane inside the group that shares the range
+  const u32 gthread = blockIdx.x * 256u + threadIdx.x;
+  const u32 s = gthread / GS;
+  const u32 tmask = (TS == 32) ? 0xffffffffu : (((1u << TS) - 1u) << (lane - tl));
+  const u32 gmask = WPS ? 0xffffffffu : tmask;
+  u32 n = 0, S = 0;
+  if (s < R)
+  {
+    n = sg.count[s];
+    S = sg.start[s];
+    if (n < nmin || n >= nmax) n = 0;
+  }
+  if (n == 0) return;  // n is uniform over the group
+  const int C4 = FULL ? TS * CH : (ld >> 2);
+  const u32* pp = perm + S;
+  const i64 id0 = (gl < n) ? pid[S + gl] : 0;  // issued early: its latency hides behind the row loads
+  const Key128 thr = qfx_threshold(n);
+  bool ok = false;
+  QfxBest best;
+  best.key.hi = 0;
+  best.key.lo = 0;
+  best.s1 = 0;
+  best.idx = 0x7fffffff;
+
+  for (int c0 = 0; c0 < C4; c0 += TS * CH)
+  {
+    i64 s1[CH * 4];
+    u64 s2[CH * 4];
+#pragma unroll
+    for (int i = 0; i < CH * 4; ++i) { s1[i] = 0; s2[i] = 0; }
+
+    u32 mine = (gl < n) ? pp[gl] : 0u;
+    for (u32 jb = 0; jb < n; jb += GS)
+    {
+      const u32 nxt = (jb + GS + gl < n) ? pp[jb + GS + gl] : 0u;  // prefetch the next block of row indexes
+      const u32 m = min((u32)GS, n - jb);
+#pragma unroll 2
+      for (u32 j0 = 0; j0 < m; j0 += TPS)
+      {
+        const u32 jj = j0 + trow;
+        const bool valid = jj < m;
+        const u32 r = __shfl_sync(gmask, mine, valid ? jj : 0u, GS);
+        if (valid)
+        {
+          const float4* rp = reinterpret_cast<const float4*>(rows + (size_t)r * ld);
+          float4 x[CH];
+#pragma unroll
+          for (int k = 0; k < CH; ++k)
+          {
+            const int c = c0 + k * TS + tl;
+            x[k] = (FULL || c < C4) ? ldg_f4_stream(rp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < CH; ++k) qfx_acc4(s1 + k * 4, s2 + k * 4, x[k], qk);
+        }
+      }
+      mine = nxt;
+    }
+    if (TPS > 1)
+    {
+      // combine the teams of the warp (integer sums: order does not matter; n < 4096 so S2 < 2^64)
+#pragma unroll
+      for (int o = TS; o < 32; o <<= 1)
+#pragma unroll
+        for (int i = 0; i < CH * 4; ++i)
+        {
+          s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+          s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+      {
+        const int d = (c0 + k * TS + tl) * 4 + e;
+        if (d < dims)
+        {
+          const Key128 key = qfx_key(n, s1[k * 4 + e], s2[k * 4 + e], 0ull);
+          ok |= !key_lt(key, thr);
+          if (qfx_better(mx != 0, key, d, best.key, best.idx))
+          {
+            best.key = key;
+            best.s1 = s1[k * 4 + e];
+            best.idx = d;
+          }
+        }
+      }
+  }
+  best = qfx_reduce<TS>(best, mx != 0, tmask);
+  int dim = best.idx;
+  float mid = qfx_mid(best.s1, n, qinv);
+  if (!__any_sync(tmask, ok))
+  {
+    const ExBest eb = welford_team<TS, CH>(rows, ld, dims, pp, n, tl, tmask, mx != 0);
+    dim = eb.idx;
+    mid = eb.mean;
+  }
+  // id sum (Stats.IdN): 32-bit halves in two 64-bit accumulators hold the Int128 sum exactly
+  u64 slo = (u32)id0;
+  i64 shi = id0 >> 32;
+  for (u32 j = gl + GS; j < n; j += GS)
+  {
+    const i64 id = pid[S + j];
+    slo += (u32)id;
+    shi += (id >> 32);
+  }
+#pragma unroll
+  for (int o = GS / 2; o > 0; o >>= 1)
+  {
+    slo += __shfl_xor_sync(gmask, slo, o);
+    shi += __shfl_xor_sync(gmask, shi, o);
+  }
+  if (gl == 0) write_split(sg, out, s, dim, mid, mean_id(slo, shi, n));
+}
+
+// Arg-max over the combined sums of one big range, by one warp.  acc: [dim][S1, S2 limb0, S2 limb1] (shared or
+// global), ids: the two id-sum words.
+__device__ __forceinline__ void finalize_big_range(const SegLevel& sg, u32 s, u32 n, const u64* acc, const u64* ids,
+                                                   int ld, int dims, double qinv, int mx, const StatsOut& out,
+                                                   const float* __restrict__ rows, const u32* __restrict__ perm, int lane)
+{
+  const Key128 thr = qfx_threshold(n);
+  bool ok = false;
+  QfxBest best;
+  best.key.hi = 0;
+  best.key.lo = 0;
+  best.s1 = 0;
+  best.idx = 0x7fffffff;
+  for (int d = lane; d < dims; d += 32)
+  {
+    const i64 s1 = (i64)acc[d * 3 + 0];
+    // S2 = limb0 + limb1 * 2^32 (each limb is a sum of 32-bit pieces, < 2^64)
+    const u64 l0 = acc[d * 3 + 1], l1 = acc[d * 3 + 2];
+    const u64 s2lo = l0 + (l1 << 32);
+    const u64 s2hi = (l1 >> 32) + ((s2lo < l0) ? 1ull : 0ull);
+    const Key128 key = qfx_key(n, s1, s2lo, s2hi);
+    ok |= !key_lt(key, thr);
+    if (qfx_better(mx != 0, key, d, best.key, best.idx))
+    {
+      best.key = key;
+      best.s1 = s1;
+      best.idx = d;
+    }
+  }
+  best = qfx_reduce<32>(best, mx != 0, 0xffffffffu);
+  int dim = best.idx;
+  float mid = qfx_mid(best.s1, n, qinv);
+  if (!__any_sync(0xffffffffu, ok))
+  {
+    // many points that the quantisation cannot tell apart: reference arithmetic, one warp (rare, slow)
+    const ExBest eb = welford_team<32, 1>(rows, ld, dims, perm + sg.start[s], n, lane, 0xffffffffu, mx != 0);
+    dim = eb.idx;
+    mid = eb.mean;
+  }
+  if (lane == 0) write_split(sg, out, s, dim, mid, mean_id(ids[0], (i64)ids[1], n));
+}
+
+// One CTA owns one chunk (VI_CHUNK rows) of one big range.  A range that fits one chunk (and one column pass) is
+// finished by its CTA straight from shared memory; otherwise the partial sums go to gacc with integer atomics
+// (order-independent, so the result does not depend on scheduling) and k_finalize_big_fast picks the split.
+// gacc per slot: [ld][S1, S2 limb0, S2 limb1] followed by the two id-sum words.
+template <int TS, int CH, bool FULL, int UNR>
+__global__ void __launch_bounds__(256, (TS * CH <= 32) ? 3 : 1)
+k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __restrict__ chunk_first, u32 nbig,
+                 const u32* __restrict__ perm, const i64* __restrict__ pid, const float* __restrict__ rows, int ld,
+                 int dims, float qk, double qinv, int mx, StatsOut out, u64* __restrict__ gacc)
+{
+  constexpr int NT = 256 / TS;          // teams per CTA
+  constexpr int PD = TS * CH * 4;       // dims per pass
+  static_assert(VI_CHUNK / NT < VI_MAX_ROWS_PER_LANE, "a lane's 64-bit S2 accumulator would overflow");
+  __shared__ u64 sacc[PD * 3 + 2];
+  __shared__ u32 sperm[VI_CHUNK];
+  const u32 bid = blockIdx.x;
+  u32 lo = 0, hi = nbig;
+  while (hi - lo > 1)
+  {
+    const u32 m = (lo + hi) >> 1;
+    if (chunk_first[m] <= bid) lo = m; else hi = m;
+  }
+  const u32 slot = lo;
+  const u32 s = big_list[slot];
+  const u32 S = sg.start[s], n = sg.count[s];
+  const u32 a = (bid - chunk_first[slot]) * VI_CHUNK;
+  const u32 b = min(n, a + VI_CHUNK);
+  const u32 m = b - a;
+  const int tl = threadIdx.x % TS, team = threadIdx.x / TS;
+  const int C4 = FULL ? TS * CH : (ld >> 2);
+  const bool whole = (n <= VI_CHUNK) && (C4 <= TS * CH);  // this CTA sees the whole range in one pass
+  const size_t gstride = (size_t)ld * 3 + 2;
+  u64* g = gacc + (size_t)slot * gstride;
+
+  for (u32 i = threadIdx.x; i < m; i += 256) sperm[i] = perm[S + a + i];
+  for (int i = threadIdx.x; i < PD * 3 + 2; i += 256) sacc[i] = 0;
+  // id sums (Stats.IdN)
+  {
+    u64 slo = 0;
+    i64 shi = 0;
+    for (u32 j = a + threadIdx.x; j < b; j += 256)
+    {
+      const i64 id = pid[S + j];
+      slo += (u32)id;
+      shi += (id >> 32);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      slo += __shfl_xor_sync(0xffffffffu, slo, o);
+      shi += __shfl_xor_sync(0xffffffffu, shi, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+    {
+      atomicAdd(&sacc[PD * 3 + 0], slo);
+      atomicAdd(&sacc[PD * 3 + 1], (u64)shi);
+    }
+  }
+
+  for (int c0 = 0; c0 < C4; c0 += TS * CH)
+  {
+    i64 s1[CH * 4];
+    u64 s2[CH * 4];
+#pragma unroll
+    for (int i = 0; i < CH * 4; ++i) { s1[i] = 0; s2[i] = 0; }
+#pragma unroll UNR
+    for (u32 j = team; j < m; j += NT)
+    {
+      const u32 r = sperm[j];
+      const float4* rp = reinterpret_cast<const float4*>(rows + (size_t)r * ld);
+      float4 x[CH];
+#pragma unroll
+      for (int k = 0; k < CH; ++k)
+      {
+        const int c = c0 + k * TS + tl;
+        x[k] = (FULL || c < C4) ? ldg_f4_stream(rp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) qfx_acc4(s1 + k * 4, s2 + k * 4, x[k], qk);
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+      {
+        const int dl = (k * TS + tl) * 4 + e;  // dim inside this pass
+        if (FULL || (c0 + k * TS + tl) < C4)
+        {
+          atomicAdd(&sacc[dl * 3 + 0], (u64)s1[k * 4 + e]);
+          atomicAdd(&sacc[dl * 3 + 1], s2[k * 4 + e] & 0xffffffffull);
+          atomicAdd(&sacc[dl * 3 + 2], s2[k * 4 + e] >> 32);
+        }
+      }
+    __syncthreads();
+    if (whole)
+    {
+      if (threadIdx.x < 32)
+        finalize_big_range(sg, s, n, sacc, sacc + PD * 3, ld, dims, qinv, mx, out, rows, perm, threadIdx.x);
+      return;
+    }
+    const int pass_dims = min(PD, (C4 - c0) * 4);
+    for (int i = threadIdx.x; i < pass_dims * 3; i += 256)
+    {
+      const u64 v = sacc[i];
+      if (v) atomicAdd(&g[(size_t)c0 * 12 + i], v);
+      sacc[i] = 0;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 2) atomicAdd(&g[(size_t)ld * 3 + threadIdx.x], sacc[PD * 3 + threadIdx.x]);
+}
+
+// warp per big range that spans several chunks (or column passes): arg-max over the sums combined in gacc
+__global__ void __launch_bounds__(256)
+k_finalize_big_fast(SegLevel sg, const u32* __restrict__ big_list, u32 nbig, const u64* __restrict__ gacc, int ld,
+                    int dims, double qinv, int mx, StatsOut out, const float* __restrict__ rows,
+                    const u32* __restrict__ perm, int single_pass)
+{
+  const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nbig) return;
+  const u32 s = big_list[warp];
+  const u32 n = sg.count[s];
+  if (single_pass && n <= VI_CHUNK) return;  // finished by its chunk CTA
+  const u64* g = gacc + (size_t)warp * ((size_t)ld * 3 + 2);
+  finalize_big_range(sg, s, n, g, g + (size_t)ld * 3, ld, dims, qinv, mx, out, rows, perm, lane);
+}

@@ -38,7 +38,7 @@ _f32p = ctypes.POINTER(ctypes.c_float)
 class BuildInfo(ctypes.Structure):
     _fields_ = [("ranges", ctypes.c_int64), ("levels", ctypes.c_int32), ("mode", ctypes.c_int32),
                 ("point_visits", ctypes.c_int64), ("kernel_launches", ctypes.c_int64), ("build_ms", ctypes.c_double),
-                ("q30_exponent", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("q_exponent", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class LevelInfo(ctypes.Structure):
@@ -53,7 +53,7 @@ ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 EXPORTS = ["vi_abi_version", "vi_create", "vi_destroy", "vi_last_error", "vi_points_reserve", "vi_points_add",
            "vi_points_add_device", "vi_points_count", "vi_build", "vi_build_levels", "vi_range_count",
            "vi_ranges_copy", "vi_textindex_copy", "vi_search", "vi_search_device", "vi_search_verify",
-           "vi_set_collective", "vi_table_device", "vi_stream"]
+           "vi_set_collective", "vi_table_device", "vi_stream", "vi_debug_divcheck"]
 
 _lib = None
 
@@ -94,6 +94,7 @@ def load_library() -> ctypes.CDLL:
     L.vi_set_collective.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ALLREDUCE_FN, vp]
     L.vi_table_device.argtypes = [vp] + [ctypes.POINTER(vp)] * 6
     L.vi_stream.argtypes = [vp]
+    L.vi_debug_divcheck.argtypes = [vp, ctypes.c_uint64, ctypes.c_int64, _i64p]
     L.vi_stream.restype = vp
     for name in EXPORTS:
         if name not in ("vi_destroy", "vi_last_error", "vi_points_count", "vi_range_count", "vi_stream",
@@ -278,6 +279,11 @@ class Context:
     def set_collective(self, rank: int, world: int, fn):
         self._cb = ALLREDUCE_FN(fn) if fn is not None else ALLREDUCE_FN()
         self._check(self._L.vi_set_collective(self._h, rank, world, self._cb, None))
+
+    def divcheck(self, seed: int, samples: int) -> int:
+        bad = ctypes.c_int64(-1)
+        self._check(self._L.vi_debug_divcheck(self._h, seed, samples, ctypes.byref(bad)))
+        return bad.value
 
     @property
     def stream(self) -> int:
