@@ -245,3 +245,22 @@ def test_mid_size_ranges_all_classes(mode):
     assert_same_table(ids, rows, mode)
     ids, rows = ds.unit_gaussian(5000, 100, seed=23)   # padded row width, guarded columns
     assert_same_table(ids, rows, mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_cpp_host_mirror_main_test(mode):
+    # cpp/main_test.cpp: Program.cs:54-66 crafted set through the C++ mirror of IndexBuilder.Build
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(vi.LIB_PATH), "main_test")
+    assert os.path.exists(exe), "make -C vector-database_b200/csrc"
+    out = subprocess.run([exe, str(mode), "256"], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for line in out.strip().splitlines():
+        r, d, bits, i = line.split(",")
+        got[int(r)] = (int(d), int(bits), int(i))
+    ids, rows = ds.one_hot(256)
+    ref = oracle.build(ids, rows, mode)
+    want = {int(r): (int(d), int(np.float32(m).view(np.uint32)), int(i))
+            for r, d, m, i in zip(ref.range_id, ref.dimension, ref.mid, ref.id)}
+    assert got == want

@@ -1,0 +1,39 @@
+// main_test.cpp -- the shape of VectorIndex.MainTest/Program.cs:9-67 over the C++ mirror: random set + the crafted
+// one-hot set through IndexBuilder::Build with a MemoryRangeStore factory.  Prints "rangeId,Dimension,Mid(bits),Id"
+// rows (Program.cs:80 CSV shape) so a test can diff them against the oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "vector_index.hpp"
+
+using namespace NesterovskyBros::VectorIndex;
+
+int main(int argc, char** argv)
+{
+  const int mode = argc > 1 ? atoi(argv[1]) : 0;
+  const int dimensions = argc > 2 ? atoi(argv[2]) : 1536;
+  std::vector<Point> input;  // Program.cs:54-66
+  for (int64_t i = 0; i < dimensions; ++i)
+  {
+    std::vector<float> v(dimensions, 0.0f);
+    v[i] = 1.0f;
+    input.emplace_back(i, std::move(v));
+  }
+  try
+  {
+    auto index = IndexBuilder::Build(input, [](int64_t, int64_t) { return std::make_unique<MemoryRangeStore>(); }, mode);
+    for (auto& [rangeId, range] : index)
+    {
+      uint32_t bits;
+      memcpy(&bits, &range.Mid, 4);
+      printf("%lld,%d,%u,%lld\n", (long long)rangeId, range.Dimension, bits, (long long)range.Id);
+    }
+  }
+  catch (const std::exception& e)
+  {
+    fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
