@@ -127,10 +127,23 @@ int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims
                      int64_t* offsets, int64_t* ids, int64_t cap, int64_t* total);
 
 /* ---- multi-GPU (one process per GPU; the host supplies the collective, e.g. torch.distributed/NCCL) ----------- */
-/* Sum-all-reduce of `count` uint64 words in DEVICE memory `buf`, in place, across all ranks.  Called by
- * vi_build (fast mode only) once per level while ranges are shared between ranks. */
+/* A multi-rank vi_build (VI_MODE_FAST only: its integer sums are order-independent) treats the points added to the
+ * `world` contexts as ONE data set in rank order (rank 0's points first).  Top levels: every rank reduces its local
+ * slice of every range and the sums meet in one all-reduce per level; then each range of level L = ceil(log2 world)+1
+ * moves to one owner rank (a single all-to-all) and the owners finish their sub-trees without communication.  After
+ * the build a context holds the rows of the shared top levels (replicated) plus the rows of the sub-trees it owns;
+ * the union over ranks is the single-rank table.  The two collectives are host callbacks on DEVICE buffers:
+ *   allreduce: sum of `count` uint64 words, in place, over all ranks;
+ *   alltoallv: rank r's send_bytes[d] bytes (consecutive in d_send) go to rank d, which receives recv_bytes[r]
+ *              bytes from rank r (consecutive in d_recv, ordered by source rank).
+ * Both return 0 on success and must have completed (stream-synchronised) when they return. */
 typedef int (*vi_allreduce_u64_fn)(void* user, void* d_buf, int64_t count);
-int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64_fn fn, void* user);
+typedef int (*vi_alltoallv_fn)(void* user, const void* d_send, const int64_t* send_bytes, void* d_recv,
+                               const int64_t* recv_bytes);
+int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64_fn allreduce,
+                      vi_alltoallv_fn alltoallv, void* user);
+/* Rows [0, *shared_rows) of this context's table are the replicated top levels; the rest belong to its sub-trees. */
+int vi_shared_rows(const vi_ctx* ctx, int64_t* shared_rows);
 
 /* ---- utilities -------------------------------------------------------------------------------------------------- */
 /* Raw device pointers of the built table for zero-copy consumers (valid until the next build/reserve/destroy). */

@@ -45,6 +45,8 @@ def lib() -> ctypes.CDLL:
         L.vio_build.restype = ctypes.c_int
         L.vio_build.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, _i64p, _f32p, ctypes.c_int,
                                 ctypes.c_int64, _i64p, _i32p, _f32p, _i64p, _i64p]
+        L.vio_build_ex.restype = ctypes.c_int
+        L.vio_build_ex.argtypes = L.vio_build.argtypes + [ctypes.c_int64, ctypes.c_int, ctypes.c_int32]
         L.vio_search_batch.restype = ctypes.c_int
         L.vio_search_batch.argtypes = [ctypes.c_int64, _i64p, _i32p, _f32p, _i64p, ctypes.c_int32,
                                        ctypes.c_int64, _f32p, ctypes.c_int64, ctypes.c_float, ctypes.c_int64,
@@ -82,8 +84,10 @@ class OracleError(Exception):
     pass
 
 
-def build(ids: np.ndarray, rows: np.ndarray, mode: int = MODE_LITERAL) -> RangeTable:
-    """IndexBuilder.Build restated (IndexBuilder.cs:23-157). rows: float32 [n, d], ids: int64 [n]."""
+def build(ids: np.ndarray, rows: np.ndarray, mode: int = MODE_LITERAL, root_rid: int = 0, root_depth: int = 0,
+          qe: int | None = None) -> RangeTable:
+    """IndexBuilder.Build restated (IndexBuilder.cs:23-157). rows: float32 [n, d], ids: int64 [n].
+    root_rid / root_depth / qe: build the sub-tree of one range with a given fixed-point exponent (multi-rank tests)."""
     rows = np.ascontiguousarray(rows, dtype=np.float32)
     ids = np.ascontiguousarray(ids, dtype=np.int64)
     assert rows.ndim == 2 and ids.shape[0] == rows.shape[0]
@@ -94,8 +98,9 @@ def build(ids: np.ndarray, rows: np.ndarray, mode: int = MODE_LITERAL) -> RangeT
     mid = np.empty(cap, np.float32)
     oid = np.empty(cap, np.int64)
     cnt = ctypes.c_int64(0)
-    rc = lib().vio_build(n, d, d, _p(ids, _i64p), _p(rows, _f32p), mode, cap, _p(rid, _i64p), _p(dim, _i32p),
-                         _p(mid, _f32p), _p(oid, _i64p), ctypes.byref(cnt))
+    rc = lib().vio_build_ex(n, d, d, _p(ids, _i64p), _p(rows, _f32p), mode, cap, _p(rid, _i64p), _p(dim, _i32p),
+                            _p(mid, _f32p), _p(oid, _i64p), ctypes.byref(cnt), root_rid, 1 if root_depth % 2 == 0 else 0,
+                            -2 ** 31 if qe is None else qe)
     if rc == -2:
         raise OverflowError("rangeId overflow (IndexBuilder.cs:99,104 checked arithmetic)")
     if rc != 0:

@@ -121,9 +121,23 @@ static inline int32_t qfx_quantise(float x, float k)
  * Output rows are written in the reference's emission order (DFS, high child popped first:
  * IndexBuilder.cs:128-129 pushes low then high onto a Stack).  Returns VIO_OK and *out_count.
  */
+/* vio_build_ex: the same walk started from an arbitrary range (root_rid, root_max = its depth is even) with a given
+ * fixed-point exponent (qe_override != INT32_MIN): what one rank of a multi-rank build does for a sub-tree it owns. */
+int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float* rows, int mode,
+                 int64_t cap, int64_t* out_range_id, int32_t* out_dim, float* out_mid, int64_t* out_id,
+                 int64_t* out_count, int64_t root_rid, int root_max, int32_t qe_override);
+
 int vio_build(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float* rows, int mode,
               int64_t cap, int64_t* out_range_id, int32_t* out_dim, float* out_mid, int64_t* out_id,
               int64_t* out_count)
+{
+  return vio_build_ex(n, d, ld, ids, rows, mode, cap, out_range_id, out_dim, out_mid, out_id, out_count, 0, 1,
+                      INT32_MIN);
+}
+
+int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float* rows, int mode,
+                 int64_t cap, int64_t* out_range_id, int32_t* out_dim, float* out_mid, int64_t* out_id,
+                 int64_t* out_count, int64_t root_rid, int root_max, int32_t qe_override)
 {
   if (n < 0 || d <= 0 || ld < d || (mode != 0 && mode != 1)) return VIO_ERR_ARG;
   *out_count = 0;
@@ -145,12 +159,12 @@ int vio_build(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const float*
   double qinv = 1.0;
   if (mode == 1)
   {
-    qe = vio_qfx_exponent(rows, n, d, ld);
+    qe = qe_override != INT32_MIN ? qe_override : vio_qfx_exponent(rows, n, d, ld);
     qk = ldexpf(1.0f, VIO_QBITS - qe);
     qinv = ldexp(1.0, qe - VIO_QBITS);
   }
 
-  work_item root = {0, 0, n, 1}; /* IndexBuilder.cs:33 */
+  work_item root = {root_rid, 0, n, root_max}; /* IndexBuilder.cs:33 : (0, points, true) */
   if (!push(&st, root)) { rc = VIO_ERR_NOMEM; goto done; }
 
   int64_t emitted = 0;

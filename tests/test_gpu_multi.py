@@ -1,0 +1,92 @@
+"""GPU, one process per GPU over NCCL: the sharded fast-mode build (vi_build.cu build_sharded) must give, as the
+union of the per-rank tables, exactly the single-rank oracle table.  Needs >= 2 GPUs (skipped otherwise)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "vector-database_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q, n, d, seed, kind):
+    import torch.distributed as dist
+    import vectorindex as vi
+    from vectorindex import synthetic as ds
+    from vectorindex.distributed import Collectives
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ids, rows = getattr(ds, kind)(n, d, seed=seed)
+    ids = ids * 3 + 7
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    if kind == "uniform" and rank == world - 1:
+        lo = hi = n  # an empty shard on the last rank ...
+    if kind == "uniform" and rank == world - 2:
+        hi = n       # ... its points go to the rank before it
+    ctx = vi.Context(rank)
+    ctx.reserve(max(hi - lo, 1), d)
+    if hi > lo:
+        ctx.add(ids[lo:hi], rows[lo:hi])
+    coll = Collectives(torch.device("cuda", rank))
+    coll.attach(ctx)
+    info = ctx.build(vi.MODE_FAST)
+    rid, dim, mid, oid = ctx.ranges()
+    shared = ctx.shared_rows
+    # p = 0 lookups of owned points against the local part of the table are not meaningful across ranks; only rows
+    q.put((rank, rid, dim, mid.view(np.uint32), oid, shared, dict(coll.calls), int(info.levels)))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("n,d,seed,kind", [(200_000, 96, 3, "unit_gaussian"), (5000, 16, 5, "uniform")])
+def test_sharded_build_equals_oracle(world, n, d, seed, kind):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import oracle
+    import torch.multiprocessing as mp
+    from vectorindex import synthetic as ds
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + world * 7 + seed
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, n, d, seed, kind)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        item = q.get(timeout=600)
+        res[item[0]] = item[1:]
+    for p in procs:
+        p.join(120)
+    union = {}
+    owned_rows = []
+    for r in range(world):
+        rid, dim, mid, oid, shared, calls, levels = res[r]
+        assert calls["alltoallv"] == 2  # rows + ids, once
+        for k in range(len(rid)):
+            val = (int(dim[k]), int(mid[k]), int(oid[k]))
+            if k < shared:
+                assert union.setdefault(int(rid[k]), val) == val  # replicated top rows agree
+            else:
+                assert int(rid[k]) not in union
+                union[int(rid[k])] = val
+        owned_rows.append(len(rid) - shared)
+    ids, rows = getattr(ds, kind)(n, d, seed=seed)
+    ids = ids * 3 + 7
+    ref = oracle.build(ids, rows, oracle.MODE_QFX)
+    want = {int(r): (int(dm), int(np.float32(m).view(np.uint32)), int(i))
+            for r, dm, m, i in zip(ref.range_id, ref.dimension, ref.mid, ref.id)}
+    assert union == want
+    assert sum(owned_rows) + res[0][4] == len(want)
+    if kind == "unit_gaussian":
+        # ownership is balanced: no rank owns more than 1.5x its fair share of the rows
+        assert max(owned_rows) <= 1.5 * len(want) / world

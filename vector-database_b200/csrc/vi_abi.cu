@@ -69,6 +69,7 @@ void vi_destroy(vi_ctx* ctx)
   free_points(ctx);
   cudaFree(ctx->q_buf); cudaFree(ctx->off_buf); cudaFree(ctx->ids_buf); cudaFree(ctx->off2_buf);
   cudaFree(ctx->ids2_buf); cudaFree(ctx->search_src); cudaFree(ctx->verify_keep);
+  cudaFree(ctx->own_rows); cudaFree(ctx->own_ids);
   cudaFree(ctx->counters);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -335,14 +336,24 @@ int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims
   return VI_OK;
 }
 
-int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64_fn fn, void* user)
+int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64_fn allreduce,
+                      vi_alltoallv_fn alltoallv, void* user)
 {
   if (!ctx) return VI_ERR_INVALID_ARG;
-  if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return ctx->fail(VI_ERR_INVALID_ARG, "bad collective");
+  if (world < 1 || world > 64 || rank < 0 || rank >= world || (world > 1 && (!allreduce || !alltoallv)))
+    return ctx->fail(VI_ERR_INVALID_ARG, "bad collective");
   ctx->rank = rank;
   ctx->world = world;
-  ctx->allreduce = fn;
-  ctx->allreduce_user = user;
+  ctx->allreduce = allreduce;
+  ctx->alltoallv = alltoallv;
+  ctx->coll_user = user;
+  return VI_OK;
+}
+
+int vi_shared_rows(const vi_ctx* ctx, int64_t* shared_rows)
+{
+  if (!ctx || !shared_rows) return VI_ERR_INVALID_ARG;
+  *shared_rows = ctx->built ? ctx->shared_rows : 0;
   return VI_OK;
 }
 

@@ -9,10 +9,14 @@
 // parent is partitioned and drop out of the position space (it is compacted every level).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include "vi_common.cuh"
 #include "vi_partition.cuh"
 #include "vi_scan.cuh"
+#include "vi_sharded.cuh"
 #include "vi_stats_exact.cuh"
 #include "vi_stats_fast.cuh"
 
@@ -125,14 +129,14 @@ void vi_free_table(vi_ctx* ctx)
   ctx->built = false;
 }
 
-static int alloc_workspace(vi_ctx* ctx)
+static int alloc_workspace(vi_ctx* ctx, int64_t n)
 {
-  const int64_t n = ctx->n;
   if (ctx->ws_n >= n && ctx->perm[0]) return VI_OK;
   vi_free_workspace(ctx);
   const size_t N = (size_t)n;
-  const size_t maxseg = N / 2 + 2;
-  const size_t maxbig = N / VI_MIN_BIG + 2;
+  // lower bounds: the multi-rank build uses these arrays as scratch for its (small) host-built tables
+  const size_t maxseg = std::max<size_t>(N / 2 + 2, 65536);
+  const size_t maxbig = std::max<size_t>(N / VI_MIN_BIG + 2, 256);
   const size_t words = N / 32 + 4;
   for (int i = 0; i < 2; ++i)
   {
@@ -157,7 +161,7 @@ static int alloc_workspace(vi_ctx* ctx)
   VI_CUDA_TRY(dalloc(&ctx->c_rows, maxseg + 1));
   VI_CUDA_TRY(dalloc(&ctx->c_actpos, maxseg + 1));
   VI_CUDA_TRY(dalloc((u64**)&ctx->scan_tmp, maxseg / SCAN_TILE + words / SCAN_TILE + 64));
-  VI_CUDA_TRY(dalloc(&ctx->gacc, maxbig * ((size_t)ctx->ld * 3 + 2)));
+  VI_CUDA_TRY(dalloc(&ctx->gacc, maxbig * ((size_t)ctx->ld * 3 + 3)));
   VI_CUDA_TRY(dalloc(&ctx->gstats, maxbig * (size_t)ctx->dims));
   VI_CUDA_TRY(dalloc(&ctx->d_absmax, (size_t)4));
   VI_CUDA_TRY(cudaMallocHost((void**)&ctx->totals, sizeof(LevelTotals)));
@@ -165,10 +169,10 @@ static int alloc_workspace(vi_ctx* ctx)
   return VI_OK;
 }
 
-static int alloc_table(vi_ctx* ctx)
+static int alloc_table(vi_ctx* ctx, int64_t n)
 {
   // 2n-1 rows when no child is ever empty; an empty child (all points on one side) adds a one-child row.
-  const int64_t cap = 2 * ctx->n + ctx->n / 8 + 1024;
+  const int64_t cap = 2 * n + n / 8 + 1024;
   if (ctx->t_cap >= cap && ctx->t_rid) return VI_OK;
   vi_free_table(ctx);
   if (cap >= (int64_t)0x7fffffff) return ctx->fail(VI_ERR_CAPACITY, "too many points for 32-bit row indexes");
@@ -181,6 +185,39 @@ static int alloc_table(vi_ctx* ctx)
   VI_CUDA_TRY(dalloc(&ctx->t_node, (size_t)cap));
   VI_CUDA_TRY(dalloc(&ctx->t_src, (size_t)cap));
   ctx->t_cap = cap;
+  return VI_OK;
+}
+
+// grows the table to hold `rows_needed` rows, keeping the first `keep` rows (multi-rank build: the shared top rows
+// exist before a rank learns how many points it will own)
+template <typename T>
+static cudaError_t regrow(T** p, size_t newcount, size_t keep, cudaStream_t st)
+{
+  T* q = nullptr;
+  cudaError_t e = cudaMalloc((void**)&q, newcount * sizeof(T) + 256);
+  if (e != cudaSuccess) return e;
+  if (keep) e = cudaMemcpyAsync(q, *p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(*p);
+  *p = q;
+  return e;
+}
+
+static int grow_table(vi_ctx* ctx, int64_t rows_needed, int64_t keep)
+{
+  if (ctx->t_cap >= rows_needed) return VI_OK;
+  if (rows_needed >= (int64_t)0x7fffffff) return ctx->fail(VI_ERR_CAPACITY, "too many points for 32-bit row indexes");
+  const size_t c = (size_t)rows_needed, k = (size_t)keep;
+  cudaStream_t st = ctx->stream;
+  VI_CUDA_TRY(regrow(&ctx->t_rid, c, k, st));
+  VI_CUDA_TRY(regrow(&ctx->t_dim, c, k, st));
+  VI_CUDA_TRY(regrow(&ctx->t_mid, c, k, st));
+  VI_CUDA_TRY(regrow(&ctx->t_id, c, k, st));
+  VI_CUDA_TRY(regrow(&ctx->t_low, c, k, st));
+  VI_CUDA_TRY(regrow(&ctx->t_high, c, k, st));
+  VI_CUDA_TRY(regrow(&ctx->t_node, c, k, st));
+  VI_CUDA_TRY(regrow(&ctx->t_src, c, k, st));
+  ctx->t_cap = rows_needed;
   return VI_OK;
 }
 
@@ -264,200 +301,188 @@ int vi_debug_divcheck_impl(vi_ctx* ctx, uint64_t seed, int64_t samples, int64_t*
 // =============================================================================================================
 // the build
 // =============================================================================================================
-int vi_build_impl(vi_ctx* ctx, int mode)
+struct BuildEnv
 {
-  const int64_t n64 = ctx->n;
-  ctx->built = false;
-  ctx->levels.clear();
-  ctx->info = vi_build_info();
-  ctx->info.mode = mode;
-  if (n64 >= (int64_t)0x7fffffff) return ctx->fail(VI_ERR_CAPACITY, "more than 2^31-2 points per context");
-  if (n64 == 0)
-  {
-    // IndexBuilder.cs:70-73: an empty range emits no row
-    ctx->t_rows = 0;
-    ctx->built = true;
-    return VI_OK;
-  }
-  int rc = alloc_table(ctx);
-  if (rc != VI_OK) return rc;
-  cudaStream_t st = ctx->stream;
-  const u32 n = (u32)n64;
-  const int ld = ctx->ld, dims = ctx->dims;
+  int mode;
+  u32 t_team, t_big, big_unroll;
+  FastShape shp;
+  int chx;
+  float qk;
+  double qinv;
+  size_t gstride;
   int64_t launches = 0;
+  std::vector<cudaEvent_t> ev;
+};
 
-  // range-size classes (see vi_stats_fast.cuh / vi_stats_exact.cuh); tunable for experiments
-  // defaults from scripts/sweep.py on 10M x 96 (profiles/r1_sweep.txt)
-  const u32 t_team = env_u32("VI_B200_T_TEAM", 32, 2, VI_MAX_ROWS_PER_LANE);
+struct LevelState
+{
+  u32 A, R, nbig, chunks, minseg, maxseg;
+  u32 row_next;  // first free table row
+  int cur;       // ping-pong index of the current level's buffers
+  int level;     // depth of the ranges in seg[cur]
+};
+
+static cudaEvent_t env_event(vi_ctx* ctx, BuildEnv& env)
+{
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, ctx->stream);
+  env.ev.push_back(e);
+  return e;
+}
+
+static void env_cleanup(BuildEnv& env)
+{
+  for (cudaEvent_t e : env.ev) cudaEventDestroy(e);
+  env.ev.clear();
+}
+
+static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
+{
+  env.mode = mode;
+  // range-size classes (see vi_stats_fast.cuh / vi_stats_exact.cuh); defaults from scripts/sweep.py on 10M x 96
+  // (profiles/r1_sweep.txt); the variables exist for such sweeps
+  env.t_team = env_u32("VI_B200_T_TEAM", 32, 2, VI_MAX_ROWS_PER_LANE);
   const u32 t_big_fast = env_u32("VI_B200_T_BIG", 1024, VI_MIN_BIG, VI_MAX_ROWS_PER_LANE);
   const u32 t_big_exact = env_u32("VI_B200_T_BIG_EXACT", 512, VI_MIN_BIG, 1u << 30);
-  const u32 t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
-  const u32 big_unroll = env_u32("VI_B200_BIG_UNROLL", 4, 1, 4);
+  env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
+  env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 4, 1, 4);
+  env.shp = fast_shape(ctx->ld);
+  env.chx = exact_chx(ctx->dims);
+  env.qk = 1.0f;
+  env.qinv = 1.0;
+  env.gstride = (size_t)ctx->ld * 3 + 3;
+}
 
-  cudaEvent_t ev_begin, ev_end;
-  VI_CUDA_TRY(cudaEventCreate(&ev_begin));
-  VI_CUDA_TRY(cudaEventCreate(&ev_end));
-  std::vector<cudaEvent_t> lev_ev;
-  auto new_event = [&]() -> cudaEvent_t
-  {
-    cudaEvent_t e;
-    cudaEventCreate(&e);
-    cudaEventRecord(e, st);
-    lev_ev.push_back(e);
-    return e;
-  };
-  auto cleanup = [&]()
-  {
-    for (cudaEvent_t e : lev_ev) cudaEventDestroy(e);
-    cudaEventDestroy(ev_begin);
-    cudaEventDestroy(ev_end);
-  };
-
-  VI_CUDA_TRY(cudaEventRecord(ev_begin, st));
-  if (n == 1)
-  {
-    k_single_point<<<1, 1, 0, st>>>(ctx->ids, ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high,
-                                    ctx->t_src);
-    k_pack_nodes<<<1, 32, 0, st>>>(ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high, ctx->t_node, 1);
-    VI_CUDA_TRY(cudaEventRecord(ev_end, st));
-    VI_CUDA_TRY(cudaStreamSynchronize(st));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev_begin, ev_end);
-    cleanup();
-    ctx->t_rows = 1;
-    ctx->built = true;
-    ctx->info.ranges = 1;
-    ctx->info.levels = 1;
-    ctx->info.kernel_launches = 2;
-    ctx->info.build_ms = ms;
-    return VI_OK;
-  }
-  rc = alloc_workspace(ctx);
-  if (rc != VI_OK) { cleanup(); return rc; }
-
-  // fast mode: quantisation exponent E with max|x| < 2^E
+static void set_q_exponent(vi_ctx* ctx, BuildEnv& env, float amax)
+{
   int qe = 0;
-  float qk = 1.0f;
-  double qinv = 1.0;
-  if (mode == VI_MODE_FAST)
-  {
-    VI_CUDA_TRY(cudaMemsetAsync(ctx->d_absmax, 0, 4, st));
-    k_absmax<<<VI_NUM_SMS * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->rows), (size_t)n * ld / 4,
-                                             (u32*)ctx->d_absmax);
-    ++launches;
-    float amax = 0.f;
-    VI_CUDA_TRY(cudaMemcpyAsync(&amax, ctx->d_absmax, 4, cudaMemcpyDeviceToHost, st));
-    VI_CUDA_TRY(cudaStreamSynchronize(st));
-    if (isinf(amax)) qe = 128;
-    else if (amax > 0.f) (void)frexpf(amax, &qe);
-    if (qe < -96) qe = -96;
-    if (qe > 128) qe = 128;
-    qk = ldexpf(1.0f, VI_QBITS - qe);
-    qinv = ldexp(1.0, qe - VI_QBITS);
-    ctx->info.q_exponent = qe;
-  }
+  if (isinf(amax)) qe = 128;
+  else if (amax > 0.f) (void)frexpf(amax, &qe);
+  if (qe < -96) qe = -96;
+  if (qe > 128) qe = 128;
+  env.qk = ldexpf(1.0f, VI_QBITS - qe);
+  env.qinv = ldexp(1.0, qe - VI_QBITS);
+  ctx->info.q_exponent = qe;
+}
 
+// local max |x| over n rows of `rows` (NaN ignored)
+static int local_absmax(vi_ctx* ctx, const float* rows, int64_t n, BuildEnv& env, float* out)
+{
+  cudaStream_t st = ctx->stream;
+  VI_CUDA_TRY(cudaMemsetAsync(ctx->d_absmax, 0, 4, st));
+  if (n > 0)
+  {
+    k_absmax<<<VI_NUM_SMS * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(rows), (size_t)n * ctx->ld / 4,
+                                             (u32*)ctx->d_absmax);
+    ++env.launches;
+  }
+  VI_CUDA_TRY(cudaMemcpyAsync(out, ctx->d_absmax, 4, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaStreamSynchronize(st));
+  return VI_OK;
+}
+
+// launches the fast-mode chunk kernel over the ranges in big_list[cur]
+static void launch_big_fast(vi_ctx* ctx, BuildEnv& env, const float* rows, int cur, u32 nbig, u32 chunks, int mx,
+                            int allow_whole)
+{
+  cudaStream_t st = ctx->stream;
+  SegLevel& sg = ctx->seg[cur];
+  StatsOut sout{ctx->t_dim, ctx->t_mid, ctx->t_id};
+  const int ld = ctx->ld, dims = ctx->dims;
+#define CALL_BIG(TS, CH, FULL)                                                                                     \
+  if (env.big_unroll >= 4)                                                                                         \
+    k_stats_big_fast<TS, CH, FULL, 4><<<chunks, 256, 0, st>>>(sg, ctx->big_list[cur], ctx->chunk_first, nbig,       \
+                                                              ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, \
+                                                              env.qinv, mx, sout, ctx->gacc, allow_whole);         \
+  else                                                                                                             \
+    k_stats_big_fast<TS, CH, FULL, 2><<<chunks, 256, 0, st>>>(sg, ctx->big_list[cur], ctx->chunk_first, nbig,       \
+                                                              ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, \
+                                                              env.qinv, mx, sout, ctx->gacc, allow_whole)
+  FAST_DISPATCH(env.shp, CALL_BIG);
+#undef CALL_BIG
+  ++env.launches;
+}
+
+// The level loop: processes seg[s.cur] (ranges of depth s.level) until no range with >= 2 points is left.
+// `rows` is the row store perm[] indexes.
+static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* rows)
+{
+  cudaStream_t st = ctx->stream;
+  const int ld = ctx->ld, dims = ctx->dims;
+  const int mode = env.mode;
   TableOut tout{ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high};
   StatsOut sout{ctx->t_dim, ctx->t_mid, ctx->t_id};
+  const u32 t_team = env.t_team, t_big = env.t_big;
+  const FastShape shp = env.shp;
+  u32* lvl_counters = ctx->counters + 16;  // u32[16..23]; [2..3] search visits, [4..5] divcheck
 
-  k_init_level0<<<(n + 255) / 256, 256, 0, st>>>(ctx->perm[0], ctx->pid[0], ctx->ids, ctx->seg_of[0], n, ctx->seg[0],
-                                                 ctx->big_list[0], ctx->t_rid, ctx->t_low, ctx->t_high);
-  ++launches;
-
-  u32 A = n, R = 1;
-  u32 nbig = n >= t_big ? 1u : 0u;
-  u32 chunks = nbig ? (n + VI_CHUNK - 1) / VI_CHUNK : 0u;
-  u32 minseg = n, maxseg = n;
-  if (nbig)
+  while (s.R > 0)
   {
-    const u32 h[2] = {0u, chunks};
-    VI_CUDA_TRY(cudaMemcpyAsync(ctx->chunk_first, h, sizeof(h), cudaMemcpyHostToDevice, st));
-  }
-  u32 row_base = 0, nrows = 1;
-  int cur = 0;
-  int level = 0;
-  const FastShape shp = fast_shape(ld);
-  const int chx = exact_chx(dims);
-  const size_t gstride = (size_t)ld * 3 + 2;
-
-  while (R > 0)
-  {
-    if (level >= VI_MAX_DEPTH)
-    {
-      cleanup();
+    if (s.level >= VI_MAX_DEPTH)
       return ctx->fail(VI_ERR_OVERFLOW, "rangeId overflow: a range at depth 62 still holds more than one point "
                                         "(IndexBuilder.cs:99 checked(rangeId * 2 + 1))");
-    }
-    const int nxt = cur ^ 1;
-    const int mx = (level & 1) == 0;  // root max = true, children !max (IndexBuilder.cs:33,128-129)
+    const int cur = s.cur, nxt = cur ^ 1;
+    const int mx = (s.level & 1) == 0;  // root max = true, children !max (IndexBuilder.cs:33,128-129)
     SegLevel& sg = ctx->seg[cur];
-    cudaEvent_t e0 = new_event();
+    const u32 A = s.A, R = s.R;
+    cudaEvent_t e0 = env_event(ctx, env);
 
     // ---- statistics + split choice -----------------------------------------------------------------------
     if (mode == VI_MODE_FAST)
     {
-      if (nbig)
+      if (s.nbig)
       {
-        VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)nbig * gstride * sizeof(u64), st));
-#define CALL_BIG(TS, CH, FULL)                                                                                         \
-  if (big_unroll >= 4)                                                                                                 \
-    k_stats_big_fast<TS, CH, FULL, 4><<<chunks, 256, 0, st>>>(sg, ctx->big_list[cur], ctx->chunk_first, nbig,           \
-                                                              ctx->perm[cur], ctx->pid[cur], ctx->rows, ld, dims, qk,   \
-                                                              qinv, mx, sout, ctx->gacc);                              \
-  else                                                                                                                 \
-    k_stats_big_fast<TS, CH, FULL, 2><<<chunks, 256, 0, st>>>(sg, ctx->big_list[cur], ctx->chunk_first, nbig, ctx->perm[cur], \
-                                                         ctx->pid[cur], ctx->rows, ld, dims, qk, qinv, mx, sout, ctx->gacc)
-        FAST_DISPATCH(shp, CALL_BIG);
-#undef CALL_BIG
-        ++launches;
+        VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)s.nbig * env.gstride * sizeof(u64), st));
+        launch_big_fast(ctx, env, rows, cur, s.nbig, s.chunks, mx, 1);
         // ranges that fit one chunk and one column pass were finished by their CTA
         const int single_pass = (ld / 4) <= shp.ts * shp.ch;
-        if (!single_pass || maxseg > VI_CHUNK)
+        if (!single_pass || s.maxseg > VI_CHUNK)
         {
-          k_finalize_big_fast<<<(nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], nbig, ctx->gacc, ld, dims,
-                                                                       qinv, mx, sout, ctx->rows, ctx->perm[cur],
-                                                                       single_pass);
-          ++launches;
+          k_finalize_big_fast<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, ctx->gacc, ld,
+                                                                         dims, env.qinv, mx, sout, rows, ctx->perm[cur],
+                                                                         single_pass, 0, nullptr);
+          ++env.launches;
         }
       }
       // warp-per-range class (teams of a warp share one range); for TS == 32 it also covers the team class
       const u32 wlo = shp.ts == 32 ? 2u : t_team;
-      if (minseg < t_big && maxseg >= wlo)
+      if (s.minseg < t_big && s.maxseg >= wlo)
       {
-#define CALL_WARP(TS, CH, FULL)                                                                                        \
-  k_stats_small_fast<TS, CH, FULL, true><<<(u32)(((u64)R * 32 + 255) / 256), 256, 0, st>>>(                             \
-      sg, R, wlo, t_big, ctx->perm[cur], ctx->pid[cur], ctx->rows, ld, dims, qk, qinv, mx, sout)
+#define CALL_WARP(TS, CH, FULL)                                                                              \
+  k_stats_small_fast<TS, CH, FULL, true><<<(u32)(((u64)R * 32 + 255) / 256), 256, 0, st>>>(                   \
+      sg, R, wlo, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout)
         FAST_DISPATCH(shp, CALL_WARP);
 #undef CALL_WARP
-        ++launches;
+        ++env.launches;
       }
-      if (shp.ts < 32 && minseg < t_team)
+      if (shp.ts < 32 && s.minseg < t_team)
       {
-#define CALL_TEAM(TS, CH, FULL)                                                                                        \
-  k_stats_small_fast<TS, CH, FULL, false><<<(u32)(((u64)R * TS + 255) / 256), 256, 0, st>>>(                            \
-      sg, R, 2u, t_team, ctx->perm[cur], ctx->pid[cur], ctx->rows, ld, dims, qk, qinv, mx, sout)
+#define CALL_TEAM(TS, CH, FULL)                                                                              \
+  k_stats_small_fast<TS, CH, FULL, false><<<(u32)(((u64)R * TS + 255) / 256), 256, 0, st>>>(                  \
+      sg, R, 2u, t_team, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout)
         FAST_DISPATCH(shp, CALL_TEAM);
 #undef CALL_TEAM
-        ++launches;
+        ++env.launches;
       }
     }
     else
     {
-      if (nbig)
+      if (s.nbig)
       {
         const u32 nblk = (u32)((dims + 31) / 32);
-        k_stats_big_exact<<<nbig * nblk, 32, 0, st>>>(sg, ctx->big_list[cur], nblk, ctx->perm[cur], ctx->rows, ld, dims,
-                                                      ctx->gstats);
-        k_finalize_big_exact<<<(nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], nbig, ctx->gstats,
-                                                                      ctx->pid[cur], dims, mx, sout);
-        launches += 2;
+        k_stats_big_exact<<<s.nbig * nblk, 32, 0, st>>>(sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, dims,
+                                                        ctx->gstats);
+        k_finalize_big_exact<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, ctx->gstats,
+                                                                        ctx->pid[cur], dims, mx, sout);
+        env.launches += 2;
       }
-      if (minseg < t_big)
+      if (s.minseg < t_big)
       {
         const u32 grid = (u32)(((u64)R * 32 + 255) / 256);
 #define CALL_EX(CHX) \
-  k_stats_small_exact<CHX><<<grid, 256, 0, st>>>(sg, R, t_big, ctx->perm[cur], ctx->pid[cur], ctx->rows, ld, dims, mx, sout)
-        switch (chx)
+  k_stats_small_exact<CHX><<<grid, 256, 0, st>>>(sg, R, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, mx, sout)
+        switch (env.chx)
         {
           case 1: CALL_EX(1); break;
           case 2: CALL_EX(2); break;
@@ -466,28 +491,27 @@ int vi_build_impl(vi_ctx* ctx, int mode)
           default: CALL_EX(8); break;
         }
 #undef CALL_EX
-        ++launches;
+        ++env.launches;
       }
     }
-    cudaEvent_t e1 = new_event();
+    cudaEvent_t e1 = env_event(ctx, env);
 
     // ---- stable partition ----------------------------------------------------------------------------------
     const u32 W = (A + 31) / 32;
-    k_flags<<<W / 8 + 1, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], ctx->rows, ld, A, ctx->fbits,
+    k_flags<<<W / 8 + 1, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], rows, ld, A, ctx->fbits,
                                        ctx->wpre);
-    ++launches;
-    scan_exclusive<u32>(ctx, ctx->wpre, W + 1, launches);
+    ++env.launches;
+    scan_exclusive<u32>(ctx, ctx->wpre, W + 1, env.launches);
     k_seg_children<<<(R + 255) / 256, 256, 0, st>>>(sg, R, ctx->wpre, ctx->fbits, ctx->seg_nlo, ctx->seg_hbase,
                                                     ctx->c_rows, ctx->c_actpos);
-    ++launches;
-    scan_exclusive<u32>(ctx, ctx->c_rows, R, launches);
-    scan_exclusive<u64>(ctx, ctx->c_actpos, R, launches);
+    ++env.launches;
+    scan_exclusive<u32>(ctx, ctx->c_rows, R, env.launches);
+    scan_exclusive<u64>(ctx, ctx->c_actpos, R, env.launches);
     {
       const u32 init[8] = {0u, 0u, 0u, 0u, 0xffffffffu, 0u, 0u, 0u};  // [0] nbig [1] err [4] minseg [5] maxseg
-      VI_CUDA_TRY(cudaMemcpyAsync(ctx->counters + 16, init, sizeof(init), cudaMemcpyHostToDevice, st));
+      VI_CUDA_TRY(cudaMemcpyAsync(lvl_counters, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
-    u32* lvl_counters = ctx->counters + 16;  // u32[16..23]; [2..3] search visits, [4..5] divcheck
-    const u32 row_base_next = row_base + nrows;
+    const u32 row_base_next = s.row_next;
     k_emit_children<<<(R + 255) / 256, 256, 0, st>>>(sg, R, ctx->seg_nlo, ctx->c_rows, ctx->c_actpos, ctx->seg[nxt],
                                                      row_base_next, (u32)ctx->t_cap, tout, ctx->big_list[nxt], t_big,
                                                      lvl_counters);
@@ -495,7 +519,7 @@ int vi_build_impl(vi_ctx* ctx, int mode)
                                                ctx->wpre, ctx->seg_nlo, ctx->seg_hbase, ctx->c_rows, ctx->c_actpos,
                                                row_base_next, ctx->perm[nxt], ctx->pid[nxt], ctx->seg_of[nxt], ctx->t_id,
                                                ctx->t_src, lvl_counters);
-    launches += 2;
+    env.launches += 2;
     const u32 big_bound = A / t_big + 1;
     u32* chunk_arr = nullptr;
     if (mode == VI_MODE_FAST)
@@ -503,24 +527,21 @@ int vi_build_impl(vi_ctx* ctx, int mode)
       chunk_arr = ctx->chunk_first;
       k_big_chunks<<<(big_bound + 255) / 256, 256, 0, st>>>(ctx->seg[nxt].count, ctx->big_list[nxt], lvl_counters,
                                                             chunk_arr, big_bound);
-      ++launches;
-      scan_exclusive<u32>(ctx, chunk_arr, big_bound, launches);
+      ++env.launches;
+      scan_exclusive<u32>(ctx, chunk_arr, big_bound, env.launches);
     }
     k_totals<<<1, 1, 0, st>>>(ctx->c_rows, ctx->c_actpos, R, lvl_counters, chunk_arr, big_bound, ctx->totals);
-    ++launches;
-    cudaEvent_t e2 = new_event();
+    ++env.launches;
+    cudaEvent_t e2 = env_event(ctx, env);
     VI_CUDA_TRY(cudaStreamSynchronize(st));
     const LevelTotals tt = *ctx->totals;
     if (tt.err)
-    {
-      cleanup();
       return ctx->fail(VI_ERR_CAPACITY, "range table capacity exceeded (degenerate input: too many one-child ranges)");
-    }
     vi_level_info li{};
-    li.level = level;
+    li.level = s.level;
     li.ranges = R;
     li.points = A;
-    li.rows_emitted = nrows;
+    li.rows_emitted = tt.rows;
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     li.stats_ms = ms;
@@ -529,40 +550,520 @@ int vi_build_impl(vi_ctx* ctx, int mode)
     ctx->levels.push_back(li);
     ctx->info.point_visits += A;
 
-    row_base = row_base_next;
-    nrows = tt.rows;
-    R = tt.segs;
-    A = tt.pos;
-    nbig = tt.nbig;
-    chunks = tt.chunks;
-    minseg = tt.minseg;
-    maxseg = tt.maxseg;
-    cur = nxt;
-    ++level;
+    s.row_next = row_base_next + tt.rows;
+    s.R = tt.segs;
+    s.A = tt.pos;
+    s.nbig = tt.nbig;
+    s.chunks = tt.chunks;
+    s.minseg = tt.minseg;
+    s.maxseg = tt.maxseg;
+    s.cur = nxt;
+    ++s.level;
   }
-  // last level's rows are all leaves (or none)
-  if (nrows > 0)
+  return VI_OK;
+}
+
+static int finish_table(vi_ctx* ctx, BuildEnv& env, u32 total_rows, cudaEvent_t ev_begin)
+{
+  cudaStream_t st = ctx->stream;
+  if (total_rows > 0)
   {
-    vi_level_info li{};
-    li.level = level;
-    li.rows_emitted = nrows;
-    ctx->levels.push_back(li);
+    k_pack_nodes<<<(total_rows + 255) / 256, 256, 0, st>>>(ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high,
+                                                           ctx->t_node, total_rows);
+    ++env.launches;
   }
-  const u32 total_rows = row_base + nrows;
-  k_pack_nodes<<<(total_rows + 255) / 256, 256, 0, st>>>(ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high,
-                                                         ctx->t_node, total_rows);
-  ++launches;
-  VI_CUDA_TRY(cudaEventRecord(ev_end, st));
+  cudaEvent_t ev_end = env_event(ctx, env);
   VI_CUDA_TRY(cudaStreamSynchronize(st));
   VI_CUDA_TRY(cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, ev_begin, ev_end);
-  cleanup();
   ctx->t_rows = total_rows;
   ctx->built = true;
   ctx->info.ranges = total_rows;
   ctx->info.levels = (int32_t)ctx->levels.size();
-  ctx->info.kernel_launches = launches;
+  ctx->info.kernel_launches = env.launches;
   ctx->info.build_ms = ms;
   return VI_OK;
+}
+
+static int build_single(vi_ctx* ctx, BuildEnv& env)
+{
+  cudaStream_t st = ctx->stream;
+  const u32 n = (u32)ctx->n;
+  cudaEvent_t ev_begin = env_event(ctx, env);
+  if (n == 1)
+  {
+    k_single_point<<<1, 1, 0, st>>>(ctx->ids, ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high,
+                                    ctx->t_src);
+    ++env.launches;
+    vi_level_info li{};
+    li.rows_emitted = 1;
+    ctx->levels.push_back(li);
+    return finish_table(ctx, env, 1, ev_begin);
+  }
+  int rc = alloc_workspace(ctx, ctx->n);
+  if (rc != VI_OK) return rc;
+  if (env.mode == VI_MODE_FAST)
+  {
+    float amax = 0.f;
+    rc = local_absmax(ctx, ctx->rows, ctx->n, env, &amax);
+    if (rc != VI_OK) return rc;
+    set_q_exponent(ctx, env, amax);
+  }
+  k_init_level0<<<(n + 255) / 256, 256, 0, st>>>(ctx->perm[0], ctx->pid[0], ctx->ids, ctx->seg_of[0], n, ctx->seg[0],
+                                                 ctx->big_list[0], ctx->t_rid, ctx->t_low, ctx->t_high);
+  ++env.launches;
+  LevelState s{};
+  s.A = n;
+  s.R = 1;
+  s.nbig = n >= env.t_big ? 1u : 0u;
+  s.chunks = s.nbig ? (n + VI_CHUNK - 1) / VI_CHUNK : 0u;
+  s.minseg = s.maxseg = n;
+  s.row_next = 1;
+  s.cur = 0;
+  s.level = 0;
+  if (s.nbig)
+  {
+    const u32 h[2] = {0u, s.chunks};
+    VI_CUDA_TRY(cudaMemcpyAsync(ctx->chunk_first, h, sizeof(h), cudaMemcpyHostToDevice, st));
+  }
+  rc = run_levels(ctx, env, s, ctx->rows);
+  if (rc != VI_OK) return rc;
+  return finish_table(ctx, env, s.row_next, ev_begin);
+}
+
+// =============================================================================================================
+// multi-rank build (protocol: include/vi_b200.h vi_set_collective, DESIGN.md "Multi-GPU build")
+// =============================================================================================================
+struct HostSeg
+{
+  u32 start, lcount;  // local slice
+  u64 gcount;         // points over all ranks
+  i64 rid;
+  u32 row;
+};
+
+template <typename T>
+static int upload(vi_ctx* ctx, T* dst, const std::vector<T>& src)
+{
+  if (src.empty()) return VI_OK;
+  VI_CUDA_TRY(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // src is a stack/heap temporary
+  return VI_OK;
+}
+
+// all-reduce (sum) of a small host vector of u64 through the device scratch `gacc`
+static int allreduce_host(vi_ctx* ctx, std::vector<u64>& v)
+{
+  if (v.empty()) return VI_OK;
+  VI_CUDA_TRY(cudaMemcpyAsync(ctx->gacc, v.data(), v.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->allreduce(ctx->coll_user, ctx->gacc, (int64_t)v.size()) != 0)
+    return ctx->fail(VI_ERR_CUDA, "all-reduce callback failed");
+  VI_CUDA_TRY(cudaMemcpyAsync(v.data(), ctx->gacc, v.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return VI_OK;
+}
+
+static int build_sharded(vi_ctx* ctx, BuildEnv& env)
+{
+  cudaStream_t st = ctx->stream;
+  const int G = ctx->world, me = ctx->rank;
+  const int ld = ctx->ld, dims = ctx->dims;
+  const u32 nloc = (u32)ctx->n;
+  cudaEvent_t ev_begin = env_event(ctx, env);
+
+  // ---- global size and quantisation exponent ----------------------------------------------------------------
+  int rc = alloc_workspace(ctx, std::max<int64_t>(ctx->n, 1024));
+  if (rc != VI_OK) return rc;
+  float amax = 0.f;
+  rc = local_absmax(ctx, ctx->rows, ctx->n, env, &amax);
+  if (rc != VI_OK) return rc;
+  std::vector<u64> v0((size_t)2 * G, 0);
+  v0[me] = nloc;
+  u32 amax_mine = 0;
+  memcpy(&amax_mine, &amax, 4);
+  v0[G + me] = amax_mine;  // non-negative floats order like their bit patterns
+  rc = allreduce_host(ctx, v0);
+  if (rc != VI_OK) return rc;
+  u64 nglobal = 0;
+  u32 amax_bits = 0;
+  for (int g = 0; g < G; ++g)
+  {
+    nglobal += v0[g];
+    amax_bits = std::max(amax_bits, (u32)v0[G + g]);
+  }
+  memcpy(&amax, &amax_bits, 4);
+  set_q_exponent(ctx, env, amax);
+  if (nglobal >= 0x7fffffffull) return ctx->fail(VI_ERR_CAPACITY, "more than 2^31-2 points");
+  if (nglobal == 0) return finish_table(ctx, env, 0, ev_begin);
+
+  // ---- phase A: shared levels -------------------------------------------------------------------------------
+  int L = 1;
+  while ((1 << (L - 1)) < G) ++L;  // L = ceil(log2 G) + 1: about 2G ranges to balance over G owners
+  std::vector<HostSeg> segs{{0u, nloc, nglobal, 0, 0u}};
+  // shared rows are assembled on the host (a few dozen rows) and uploaded at the end of the phase
+  std::vector<i64> h_rid{0};
+  std::vector<int> h_low{-1}, h_high{-1}, h_leaf{nglobal == 1 ? 1 : 0};
+  u32 T = 1;  // shared rows so far
+  int cur = 0;
+  int level = 0;
+  if (nloc > 0)
+  {
+    k_init_level0<<<(nloc + 255) / 256, 256, 0, st>>>(ctx->perm[0], ctx->pid[0], ctx->ids, ctx->seg_of[0], nloc,
+                                                      ctx->seg[0], ctx->big_list[0], ctx->t_rid, ctx->t_low, ctx->t_high);
+    ++env.launches;
+  }
+  u64* leaf_ids = ctx->c_actpos;  // scratch (unused by the shared phase): ids of shared leaf rows, owner writes
+  VI_CUDA_TRY(cudaMemsetAsync(leaf_ids, 0, 4096 * sizeof(u64), st));
+  if (nglobal == 1)
+  {
+    if (nloc == 1)
+      VI_CUDA_TRY(cudaMemcpyAsync(leaf_ids, ctx->ids, 8, cudaMemcpyDeviceToDevice, st));
+    segs.clear();
+  }
+  StatsOut sout{ctx->t_dim, ctx->t_mid, ctx->t_id};
+  u32* lvl_counters = ctx->counters + 16;
+
+  for (; level < L && !segs.empty(); ++level)
+  {
+    if (level >= VI_MAX_DEPTH) return ctx->fail(VI_ERR_OVERFLOW, "rangeId overflow (IndexBuilder.cs:99)");
+    const int nxt = cur ^ 1;
+    const int mx = (level & 1) == 0;
+    const u32 R = (u32)segs.size();
+    const u32 T_before = T;
+    SegLevel& sg = ctx->seg[cur];
+    cudaEvent_t e0 = env_event(ctx, env);
+    // range list of this level (identical on every rank except for the local slices)
+    std::vector<u32> h_start(R), h_count(R), h_row(R), h_big(R), h_cf(R + 1);
+    std::vector<i64> h_srid(R);
+    u32 A = 0, chunks = 0;
+    for (u32 i = 0; i < R; ++i)
+    {
+      h_start[i] = segs[i].start;
+      h_count[i] = segs[i].lcount;
+      h_row[i] = segs[i].row;
+      h_srid[i] = segs[i].rid;
+      h_big[i] = i;
+      h_cf[i] = chunks;
+      chunks += (segs[i].lcount + VI_CHUNK - 1) / VI_CHUNK;
+      A += segs[i].lcount;
+    }
+    h_cf[R] = chunks;
+    if ((rc = upload(ctx, sg.start, h_start)) || (rc = upload(ctx, sg.count, h_count)) || (rc = upload(ctx, sg.row, h_row)) ||
+        (rc = upload(ctx, sg.rid, h_srid)) || (rc = upload(ctx, ctx->big_list[cur], h_big)) ||
+        (rc = upload(ctx, ctx->chunk_first, h_cf)))
+      return rc;
+    // local sums of every range -> gacc, one all-reduce, identical split on every rank
+    VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)R * env.gstride * sizeof(u64), st));
+    if (chunks > 0) launch_big_fast(ctx, env, ctx->rows, cur, R, chunks, mx, 0);
+    VI_CUDA_TRY(cudaStreamSynchronize(st));
+    if (ctx->allreduce(ctx->coll_user, ctx->gacc, (int64_t)((size_t)R * env.gstride)) != 0)
+      return ctx->fail(VI_ERR_CUDA, "all-reduce callback failed");
+    VI_CUDA_TRY(cudaMemsetAsync(lvl_counters, 0, 32, st));
+    k_finalize_big_fast<<<(R * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], R, ctx->gacc, ld, dims, env.qinv,
+                                                              mx, sout, ctx->rows, ctx->perm[cur], 0, 1, lvl_counters + 1);
+    ++env.launches;
+    cudaEvent_t e1 = env_event(ctx, env);
+    // local partition flags and child sizes
+    std::vector<u32> h_nlo(R, 0);
+    if (A > 0)
+    {
+      const u32 W = (A + 31) / 32;
+      k_flags<<<W / 8 + 1, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], ctx->rows, ld, A, ctx->fbits,
+                                         ctx->wpre);
+      ++env.launches;
+      scan_exclusive<u32>(ctx, ctx->wpre, W + 1, env.launches);
+      k_seg_children<<<(R + 255) / 256, 256, 0, st>>>(sg, R, ctx->wpre, ctx->fbits, ctx->seg_nlo, ctx->seg_hbase,
+                                                      ctx->c_rows, ctx->c_actpos + 4096);
+      ++env.launches;
+      VI_CUDA_TRY(cudaMemcpyAsync(h_nlo.data(), ctx->seg_nlo, R * 4, cudaMemcpyDeviceToHost, st));
+    }
+    u32 errflag = 0;
+    VI_CUDA_TRY(cudaMemcpyAsync(&errflag, lvl_counters + 1, 4, cudaMemcpyDeviceToHost, st));
+    VI_CUDA_TRY(cudaStreamSynchronize(st));
+    if (errflag)
+      return ctx->fail(VI_ERR_STATE, "multi-rank build: a range of the shared top levels is too tightly clustered for the "
+                                     "fixed-point statistics (its float32 fallback needs all rows on one rank)");
+    std::vector<u64> cnt((size_t)2 * R);
+    for (u32 i = 0; i < R; ++i)
+    {
+      const u32 llo = segs[i].lcount ? h_nlo[i] : 0u;
+      cnt[2 * i] = llo;
+      cnt[2 * i + 1] = segs[i].lcount - llo;
+    }
+    std::vector<u64> gcnt = cnt;
+    if ((rc = allreduce_host(ctx, gcnt))) return rc;
+    // children: rows, leaves, next-level ranges, local destinations (same order as the single-rank builder:
+    // by range, low child before high child)
+    std::vector<HostSeg> next;
+    std::vector<u32> lo_dst(R, VI_NONE), hi_dst(R, VI_NONE), lo_seg(R, 0), hi_seg(R, 0);
+    std::vector<int> lo_leaf(R, -1), hi_leaf(R, -1);
+    u32 npos = 0;
+    for (u32 i = 0; i < R; ++i)
+    {
+      for (int side = 0; side < 2; ++side)
+      {
+        const u64 g = gcnt[2 * i + side];
+        const u32 l = (u32)cnt[2 * i + side];
+        if (g == 0) continue;  // empty range: no row (IndexBuilder.cs:70-73)
+        const u32 row = T++;
+        h_rid.push_back(segs[i].rid * 2 + 1 + side);
+        h_low.push_back(-1);
+        h_high.push_back(-1);
+        h_leaf.push_back(g == 1 ? 1 : 0);
+        (side ? h_high : h_low)[segs[i].row] = (int)row;
+        if (g == 1)
+          (side ? hi_leaf : lo_leaf)[i] = (int)row;
+        else
+        {
+          (side ? hi_dst : lo_dst)[i] = npos;
+          (side ? hi_seg : lo_seg)[i] = (u32)next.size();
+          next.push_back({npos, l, g, segs[i].rid * 2 + 1 + side, row});
+          npos += l;
+        }
+      }
+    }
+    if (T >= 4096) return ctx->fail(VI_ERR_CAPACITY, "too many shared rows");
+    if (A > 0)
+    {
+      u32* d = ctx->c_rows;  // scratch for the six per-range arrays
+      if ((rc = upload(ctx, d, lo_dst)) || (rc = upload(ctx, d + R, hi_dst)) || (rc = upload(ctx, d + 2 * R, lo_seg)) ||
+          (rc = upload(ctx, d + 3 * R, hi_seg)) || (rc = upload(ctx, (int*)(d + 4 * R), lo_leaf)) ||
+          (rc = upload(ctx, (int*)(d + 5 * R), hi_leaf)))
+        return rc;
+      ShScatter sc{d, d + R, d + 2 * R, d + 3 * R, (const int*)(d + 4 * R), (const int*)(d + 5 * R)};
+      k_scatter_shared<<<(A + 255) / 256, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], A, ctx->fbits,
+                                                        ctx->wpre, ctx->seg_hbase, sc, ctx->perm[nxt], ctx->pid[nxt],
+                                                        ctx->seg_of[nxt], leaf_ids, ctx->t_src);
+      ++env.launches;
+    }
+    cudaEvent_t e2 = env_event(ctx, env);
+    VI_CUDA_TRY(cudaStreamSynchronize(st));
+    vi_level_info li{};
+    li.level = level;
+    li.ranges = R;
+    li.points = A;  // local points visited
+    li.rows_emitted = (int64_t)T - (int64_t)T_before;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    li.stats_ms = ms;
+    cudaEventElapsedTime(&ms, e1, e2);
+    li.partition_ms = ms;
+    ctx->levels.push_back(li);
+    ctx->info.point_visits += A;
+    segs.swap(next);
+    cur = nxt;
+  }
+
+  // shared rows: host-assembled columns + leaf ids (owner wrote, everyone sums)
+  {
+    std::vector<u64> lid(T, 0);
+    VI_CUDA_TRY(cudaMemcpyAsync(lid.data(), leaf_ids, T * 8, cudaMemcpyDeviceToHost, st));
+    VI_CUDA_TRY(cudaStreamSynchronize(st));
+    if ((rc = allreduce_host(ctx, lid))) return rc;
+    if ((rc = upload(ctx, ctx->t_rid, h_rid)) || (rc = upload(ctx, ctx->t_low, h_low)) || (rc = upload(ctx, ctx->t_high, h_high)))
+      return rc;
+    for (u32 r = 0; r < T; ++r)
+      if (h_leaf[r])
+      {
+        const int dimv = -1;
+        const float midv = 0.f;
+        const i64 idv = (i64)lid[r];
+        VI_CUDA_TRY(cudaMemcpyAsync(ctx->t_dim + r, &dimv, 4, cudaMemcpyHostToDevice, st));
+        VI_CUDA_TRY(cudaMemcpyAsync(ctx->t_mid + r, &midv, 4, cudaMemcpyHostToDevice, st));
+        VI_CUDA_TRY(cudaMemcpyAsync(ctx->t_id + r, &idv, 8, cudaMemcpyHostToDevice, st));
+        VI_CUDA_TRY(cudaStreamSynchronize(st));
+      }
+  }
+  ctx->shared_rows = T;
+
+  // ---- phase B: ownership exchange --------------------------------------------------------------------------
+  const u32 RL = (u32)segs.size();
+  cudaFree(ctx->own_rows); ctx->own_rows = nullptr;
+  cudaFree(ctx->own_ids); ctx->own_ids = nullptr;
+  ctx->own_n = 0;
+  LevelState s{};
+  s.row_next = T;
+  s.level = level;
+  s.cur = 0;
+  if (RL > 0)
+  {
+    // who holds how much of each range
+    std::vector<u64> mat((size_t)G * RL, 0);
+    for (u32 i = 0; i < RL; ++i) mat[(size_t)me * RL + i] = segs[i].lcount;
+    if ((rc = allreduce_host(ctx, mat))) return rc;
+    // owners: largest range first to the least loaded rank (ties: lower range index, lower rank)
+    std::vector<u32> order(RL), owner(RL);
+    for (u32 i = 0; i < RL; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return segs[a].gcount > segs[b].gcount; });
+    std::vector<u64> load(G, 0);
+    for (u32 i : order)
+    {
+      int best = 0;
+      for (int g = 1; g < G; ++g)
+        if (load[g] < load[best]) best = g;
+      owner[i] = (u32)best;
+      load[best] += segs[i].gcount;
+    }
+    // send layout: by destination rank, then range index, then local position
+    std::vector<u32> send_base(RL, 0);
+    std::vector<int64_t> send_rows_n(G, 0), recv_rows_n(G, 0);
+    u32 off = 0;
+    for (int d = 0; d < G; ++d)
+      for (u32 i = 0; i < RL; ++i)
+        if (owner[i] == (u32)d)
+        {
+          send_base[i] = off;
+          off += segs[i].lcount;
+          send_rows_n[d] += segs[i].lcount;
+        }
+    u64 nown = 0;
+    for (int g = 0; g < G; ++g)
+      for (u32 i = 0; i < RL; ++i)
+        if (owner[i] == (u32)me)
+        {
+          recv_rows_n[g] += (int64_t)mat[(size_t)g * RL + i];
+          nown += mat[(size_t)g * RL + i];
+        }
+    float* send_rows = nullptr;
+    i64* send_ids = nullptr;
+    const size_t nsend = std::max<size_t>(nloc, 1), nrecv = std::max<size_t>((size_t)nown, 1);
+    VI_CUDA_TRY(cudaMalloc((void**)&send_rows, nsend * ld * sizeof(float)));
+    cudaError_t ce = cudaMalloc((void**)&send_ids, nsend * sizeof(i64));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&ctx->own_rows, nrecv * ld * sizeof(float) + 256);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&ctx->own_ids, nrecv * sizeof(i64) + 256);
+    if (ce != cudaSuccess)
+    {
+      cudaFree(send_rows); cudaFree(send_ids);
+      return ctx->fail_cuda(ce, "cudaMalloc(exchange buffers)", __FILE__, __LINE__);
+    }
+    u32 A = 0;
+    for (u32 i = 0; i < RL; ++i) A += segs[i].lcount;
+    if (A > 0)
+    {
+      // seg[cur] of the last shared level still describes local slices: refresh starts/counts for the pack kernel
+      std::vector<u32> h_start(RL), h_count(RL);
+      for (u32 i = 0; i < RL; ++i) { h_start[i] = segs[i].start; h_count[i] = segs[i].lcount; }
+      if ((rc = upload(ctx, ctx->seg[cur].start, h_start)) || (rc = upload(ctx, ctx->seg[cur].count, h_count)) ||
+          (rc = upload(ctx, ctx->c_rows, send_base)))
+        return rc;
+      const size_t threads = (size_t)A * (ld / 4);
+      k_pack_rows<<<(u32)((threads + 255) / 256), 256, 0, st>>>(ctx->seg[cur], ctx->seg_of[cur], ctx->perm[cur],
+                                                                ctx->pid[cur], ctx->rows, ld, A, ctx->c_rows, send_rows,
+                                                                send_ids);
+      ++env.launches;
+    }
+    VI_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<int64_t> sb(G), rb(G);
+    for (int g = 0; g < G; ++g) { sb[g] = send_rows_n[g] * ld * 4; rb[g] = recv_rows_n[g] * ld * 4; }
+    int cerr = ctx->alltoallv(ctx->coll_user, send_rows, sb.data(), ctx->own_rows, rb.data());
+    for (int g = 0; g < G; ++g) { sb[g] = send_rows_n[g] * 8; rb[g] = recv_rows_n[g] * 8; }
+    if (cerr == 0) cerr = ctx->alltoallv(ctx->coll_user, send_ids, sb.data(), ctx->own_ids, rb.data());
+    cudaFree(send_rows);
+    cudaFree(send_ids);
+    if (cerr != 0) return ctx->fail(VI_ERR_CUDA, "all-to-all callback failed");
+    ctx->own_n = (int64_t)nown;
+
+    // ---- phase C: forest of owned ranges, pieces in source-rank order (= global stable order) --------------
+    rc = alloc_workspace(ctx, std::max<int64_t>((int64_t)nown, 1024));
+    if (rc != VI_OK) return rc;
+    rc = grow_table(ctx, (int64_t)(2 * nown + nown / 8 + 1024 + T), T);
+    if (rc != VI_OK) return rc;
+    std::vector<u32> piece_dst, piece_src, piece_seg, f_start, f_count, f_row, f_big;
+    std::vector<i64> f_rid;
+    std::vector<u32> src_off(G, 0);  // running offset inside each source's block of the receive buffer
+    {
+      u32 acc = 0;
+      for (int g = 0; g < G; ++g) { src_off[g] = acc; acc += (u32)recv_rows_n[g]; }
+    }
+    u32 pos = 0, minseg = 0xffffffffu, maxseg = 0, chunks = 0;
+    std::vector<u32> f_cf;
+    for (u32 i = 0; i < RL; ++i)
+    {
+      if (owner[i] != (u32)me) continue;
+      const u32 fs = (u32)f_start.size();
+      f_start.push_back(pos);
+      f_count.push_back((u32)segs[i].gcount);
+      f_rid.push_back(segs[i].rid);
+      f_row.push_back(segs[i].row);
+      for (int g = 0; g < G; ++g)
+      {
+        const u32 len = (u32)mat[(size_t)g * RL + i];
+        if (len == 0) continue;
+        piece_dst.push_back(pos);
+        piece_src.push_back(src_off[g]);
+        piece_seg.push_back(fs);
+        pos += len;
+        src_off[g] += len;
+      }
+      const u32 c = (u32)segs[i].gcount;
+      minseg = std::min(minseg, c);
+      maxseg = std::max(maxseg, c);
+      if (c >= env.t_big)
+      {
+        f_big.push_back(fs);
+        f_cf.push_back(chunks);
+        chunks += (c + VI_CHUNK - 1) / VI_CHUNK;
+      }
+    }
+    f_cf.push_back(chunks);
+    s.A = pos;
+    s.R = (u32)f_start.size();
+    s.nbig = (u32)f_big.size();
+    s.chunks = chunks;
+    s.minseg = minseg;
+    s.maxseg = maxseg;
+    if (s.R > 0)
+    {
+      SegLevel& f = ctx->seg[0];
+      u32* d = ctx->c_rows;
+      const u32 np = (u32)piece_dst.size();
+      if ((rc = upload(ctx, f.start, f_start)) || (rc = upload(ctx, f.count, f_count)) || (rc = upload(ctx, f.rid, f_rid)) ||
+          (rc = upload(ctx, f.row, f_row)) || (rc = upload(ctx, ctx->big_list[0], f_big)) ||
+          (rc = upload(ctx, ctx->chunk_first, f_cf)) || (rc = upload(ctx, d, piece_dst)) ||
+          (rc = upload(ctx, d + np, piece_src)) || (rc = upload(ctx, d + 2 * np, piece_seg)))
+        return rc;
+      k_forest_init<<<(s.A + 255) / 256, 256, 0, st>>>(s.A, np, d, d + np, d + 2 * np, ctx->own_ids, ctx->perm[0],
+                                                       ctx->pid[0], ctx->seg_of[0]);
+      ++env.launches;
+      rc = run_levels(ctx, env, s, ctx->own_rows);
+      if (rc != VI_OK) return rc;
+    }
+  }
+  return finish_table(ctx, env, s.row_next, ev_begin);
+}
+
+int vi_build_impl(vi_ctx* ctx, int mode)
+{
+  const int64_t n64 = ctx->n;
+  ctx->built = false;
+  ctx->shared_rows = 0;
+  ctx->levels.clear();
+  ctx->info = vi_build_info();
+  ctx->info.mode = mode;
+  if (n64 >= (int64_t)0x7fffffff) return ctx->fail(VI_ERR_CAPACITY, "more than 2^31-2 points per context");
+  BuildEnv env;
+  env_init(ctx, env, mode);
+  int rc;
+  if (ctx->world > 1)
+  {
+    // sized for the local shard; grown once the rank knows how many points it owns (build_sharded phase C)
+    rc = alloc_table(ctx, std::max<int64_t>(n64, 4096));
+    if (rc == VI_OK) rc = build_sharded(ctx, env);
+  }
+  else if (n64 == 0)
+  {
+    // IndexBuilder.cs:70-73: an empty range emits no row
+    ctx->t_rows = 0;
+    ctx->built = true;
+    rc = VI_OK;
+  }
+  else
+  {
+    rc = alloc_table(ctx, n64);
+    if (rc == VI_OK) rc = build_single(ctx, env);
+  }
+  env_cleanup(env);
+  return rc;
 }

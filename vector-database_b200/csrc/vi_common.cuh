@@ -116,7 +116,12 @@ struct vi_ctx
   // collective
   int rank = 0, world = 1;
   vi_allreduce_u64_fn allreduce = nullptr;
-  void* allreduce_user = nullptr;
+  vi_alltoallv_fn alltoallv = nullptr;
+  void* coll_user = nullptr;
+  int64_t shared_rows = 0;      // rows of the replicated top levels (multi-rank build), else 0
+  float* own_rows = nullptr;    // multi-rank build: rows / ids of the ranges this rank owns (replace rows/ids as the
+  i64* own_ids = nullptr;       // data the table's t_src refers to)
+  int64_t own_n = 0;
 
   int fail(int code, const std::string& msg)
   {

@@ -240,7 +240,8 @@ k_stats_small_fast(SegLevel sg, u32 R, u32 nmin, u32 nmax, const u32* __restrict
 // global), ids: the two id-sum words.
 __device__ __forceinline__ void finalize_big_range(const SegLevel& sg, u32 s, u32 n, const u64* acc, const u64* ids,
                                                    int ld, int dims, double qinv, int mx, const StatsOut& out,
-                                                   const float* __restrict__ rows, const u32* __restrict__ perm, int lane)
+                                                   const float* __restrict__ rows, const u32* __restrict__ perm, int lane,
+                                                   u32* __restrict__ no_fallback_err = nullptr)
 {
   const Key128 thr = qfx_threshold(n);
   bool ok = false;
@@ -270,6 +271,11 @@ __device__ __forceinline__ void finalize_big_range(const SegLevel& sg, u32 s, u3
   float mid = qfx_mid(best.s1, n, qinv);
   if (!__any_sync(0xffffffffu, ok))
   {
+    if (no_fallback_err)
+    {
+      if (lane == 0) *no_fallback_err = 1u;
+      return;
+    }
     // many points that the quantisation cannot tell apart: reference arithmetic, one warp (rare, slow)
     const ExBest eb = welford_team<32, 1>(rows, ld, dims, perm + sg.start[s], n, lane, 0xffffffffu, mx != 0);
     dim = eb.idx;
@@ -286,12 +292,12 @@ template <int TS, int CH, bool FULL, int UNR>
 __global__ void __launch_bounds__(256, (TS * CH <= 32) ? 3 : 1)
 k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __restrict__ chunk_first, u32 nbig,
                  const u32* __restrict__ perm, const i64* __restrict__ pid, const float* __restrict__ rows, int ld,
-                 int dims, float qk, double qinv, int mx, StatsOut out, u64* __restrict__ gacc)
+                 int dims, float qk, double qinv, int mx, StatsOut out, u64* __restrict__ gacc, int allow_whole)
 {
   constexpr int NT = 256 / TS;          // teams per CTA
   constexpr int PD = TS * CH * 4;       // dims per pass
   static_assert(VI_CHUNK / NT < VI_MAX_ROWS_PER_LANE, "a lane's 64-bit S2 accumulator would overflow");
-  __shared__ u64 sacc[PD * 3 + 2];
+  __shared__ u64 sacc[PD * 3 + 3];
   __shared__ u32 sperm[VI_CHUNK];
   const u32 bid = blockIdx.x;
   u32 lo = 0, hi = nbig;
@@ -308,12 +314,14 @@ k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __res
   const u32 m = b - a;
   const int tl = threadIdx.x % TS, team = threadIdx.x / TS;
   const int C4 = FULL ? TS * CH : (ld >> 2);
-  const bool whole = (n <= VI_CHUNK) && (C4 <= TS * CH);  // this CTA sees the whole range in one pass
-  const size_t gstride = (size_t)ld * 3 + 2;
+  // this CTA sees the whole range in one pass (never in the shared phase of a multi-rank build: the range's
+  // other slices live on other ranks and the sums must meet in gacc)
+  const bool whole = allow_whole && (n <= VI_CHUNK) && (C4 <= TS * CH);
+  const size_t gstride = (size_t)ld * 3 + 3;
   u64* g = gacc + (size_t)slot * gstride;
 
   for (u32 i = threadIdx.x; i < m; i += 256) sperm[i] = perm[S + a + i];
-  for (int i = threadIdx.x; i < PD * 3 + 2; i += 256) sacc[i] = 0;
+  for (int i = threadIdx.x; i < PD * 3 + 3; i += 256) sacc[i] = 0;
   // id sums (Stats.IdN)
   {
     u64 slo = 0;
@@ -389,20 +397,23 @@ k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __res
     __syncthreads();
   }
   if (threadIdx.x < 2) atomicAdd(&g[(size_t)ld * 3 + threadIdx.x], sacc[PD * 3 + threadIdx.x]);
+  if (threadIdx.x == 2) atomicAdd(&g[(size_t)ld * 3 + 2], (u64)m);  // local point count of this chunk
 }
 
 // warp per big range that spans several chunks (or column passes): arg-max over the sums combined in gacc
 __global__ void __launch_bounds__(256)
 k_finalize_big_fast(SegLevel sg, const u32* __restrict__ big_list, u32 nbig, const u64* __restrict__ gacc, int ld,
                     int dims, double qinv, int mx, StatsOut out, const float* __restrict__ rows,
-                    const u32* __restrict__ perm, int single_pass)
+                    const u32* __restrict__ perm, int single_pass, int shared, u32* __restrict__ err)
 {
   const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= nbig) return;
   const u32 s = big_list[warp];
-  const u32 n = sg.count[s];
-  if (single_pass && n <= VI_CHUNK) return;  // finished by its chunk CTA
-  const u64* g = gacc + (size_t)warp * ((size_t)ld * 3 + 2);
-  finalize_big_range(sg, s, n, g, g + (size_t)ld * 3, ld, dims, qinv, mx, out, rows, perm, lane);
+  const u64* g = gacc + (size_t)warp * ((size_t)ld * 3 + 3);
+  // shared phase of a multi-rank build: n is the all-reduced (global) count and the float32 fallback, which needs
+  // the range's rows in global order, is not available: a poorly resolved range is reported as an error
+  const u32 n = shared ? (u32)g[(size_t)ld * 3 + 2] : sg.count[s];
+  if (!shared && single_pass && n <= VI_CHUNK) return;  // finished by its chunk CTA
+  finalize_big_range(sg, s, n, g, g + (size_t)ld * 3, ld, dims, qinv, mx, out, rows, perm, lane, shared ? err : nullptr);
 }

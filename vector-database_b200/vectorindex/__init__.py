@@ -48,12 +48,13 @@ class LevelInfo(ctypes.Structure):
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
+ALLTOALLV_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, _i64p, ctypes.c_void_p, _i64p)
 
 # every symbol include/vi_b200.h declares
 EXPORTS = ["vi_abi_version", "vi_create", "vi_destroy", "vi_last_error", "vi_points_reserve", "vi_points_add",
            "vi_points_add_device", "vi_points_count", "vi_build", "vi_build_levels", "vi_range_count",
            "vi_ranges_copy", "vi_textindex_copy", "vi_search", "vi_search_device", "vi_search_verify",
-           "vi_set_collective", "vi_table_device", "vi_stream", "vi_debug_divcheck"]
+           "vi_set_collective", "vi_shared_rows", "vi_table_device", "vi_stream", "vi_debug_divcheck"]
 
 _lib = None
 
@@ -91,7 +92,8 @@ def load_library() -> ctypes.CDLL:
                                    _i64p, _i64p]
     L.vi_search_verify.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_float, _i64p,
                                    _i64p, ctypes.c_int64, _i64p]
-    L.vi_set_collective.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ALLREDUCE_FN, vp]
+    L.vi_set_collective.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ALLREDUCE_FN, ALLTOALLV_FN, vp]
+    L.vi_shared_rows.argtypes = [vp, _i64p]
     L.vi_table_device.argtypes = [vp] + [ctypes.POINTER(vp)] * 6
     L.vi_stream.argtypes = [vp]
     L.vi_debug_divcheck.argtypes = [vp, ctypes.c_uint64, ctypes.c_int64, _i64p]
@@ -276,9 +278,32 @@ class Context:
         self._check(rc)
         return total.value, visits.value
 
-    def set_collective(self, rank: int, world: int, fn):
-        self._cb = ALLREDUCE_FN(fn) if fn is not None else ALLREDUCE_FN()
-        self._check(self._L.vi_set_collective(self._h, rank, world, self._cb, None))
+    def set_collective(self, rank: int, world: int, allreduce, alltoallv):
+        """Registers the two collectives of a multi-rank build (see vectorindex.distributed).
+        allreduce(ptr, count) and alltoallv(send_ptr, send_bytes[world], recv_ptr, recv_bytes[world]) get raw device
+        pointers and return 0 on success."""
+        def _ar(user, buf, count):
+            try:
+                return int(allreduce(buf, count) or 0)
+            except Exception as e:  # an exception must not cross the C boundary
+                print(f"allreduce callback failed: {e!r}")
+                return 1
+
+        def _a2a(user, send, sbytes, recv, rbytes):
+            try:
+                return int(alltoallv(send, [sbytes[i] for i in range(world)], recv, [rbytes[i] for i in range(world)]) or 0)
+            except Exception as e:
+                print(f"alltoallv callback failed: {e!r}")
+                return 1
+
+        self._cb = (ALLREDUCE_FN(_ar), ALLTOALLV_FN(_a2a))  # keep the thunks alive
+        self._check(self._L.vi_set_collective(self._h, rank, world, self._cb[0], self._cb[1], None))
+
+    @property
+    def shared_rows(self) -> int:
+        k = ctypes.c_int64(0)
+        self._check(self._L.vi_shared_rows(self._h, ctypes.byref(k)))
+        return k.value
 
     def divcheck(self, seed: int, samples: int) -> int:
         bad = ctypes.c_int64(-1)
