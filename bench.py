@@ -35,6 +35,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, torchrun notices), so
+# fd 1 is pointed at stderr for the whole run and the result line is written to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -164,7 +186,7 @@ def run_reference(args):
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": v, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_multi(args, rank, world, local):
@@ -220,6 +242,42 @@ def run_multi(args, rank, world, local):
     stats_ms = sum(l.stats_ms for l in levels)
     peak, peak_src = peaks()
 
+    # ---- search: replicate the table, shard the query batch (configs[3]) ------------------------------------------
+    search = None
+    if not args.no_search:
+        sync_all()
+        t0 = time.perf_counter()
+        ctx.replicate()
+        sync_all()
+        trep = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(trep, op=dist.ReduceOp.MAX)
+        nq = args.queries // world
+        q_d = gen_queries(rows_d, nq, seed=77 + rank)
+        offs_d = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+        search = {"replicate_ms": float(trep.item()), "table_rows": int(ctx.range_count), "queries_per_gpu": nq}
+        for p in (0.0, 0.01):
+            total, visits = ctx.search_device(q_d.data_ptr(), nq, DIMS, p, offs_d.data_ptr(), 0, 0)
+            ids_out = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+            for _ in range(2):
+                ctx.search_device(q_d.data_ptr(), nq, DIMS, p, offs_d.data_ptr(), ids_out.data_ptr(), total)
+            sync_all()
+            reps = 3
+            ea = torch.cuda.Event(enable_timing=True)
+            eb = torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            for _ in range(reps):
+                ctx.search_device(q_d.data_ptr(), nq, DIMS, p, offs_d.data_ptr(), ids_out.data_ptr(), total)
+            eb.record(stream)
+            sync_all()
+            tms = torch.tensor([ea.elapsed_time(eb) / reps], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            tot = torch.tensor([float(total), float(visits)], device=dev, dtype=torch.float64)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            search[f"p={p}"] = {"queries_per_sec": nq * world / (float(tms.item()) / 1e3), "ms": float(tms.item()),
+                                "queries": nq * world, "candidates": int(tot[0].item()), "visits": int(tot[1].item())}
+            del ids_out
+        del q_d, offs_d
+
     # e2e: host shard -> H2D -> sharded build -> D2H of this rank's part of the table
     rows_h = torch.empty((m, DIMS), dtype=torch.float32, pin_memory=True)
     ids_h = torch.empty((m,), dtype=torch.int64, pin_memory=True)
@@ -268,10 +326,10 @@ def run_multi(args, rank, world, local):
                           "h2d_bytes_per_step": n * (4 * DIMS + 8), "d2h_bytes_per_step": int(d2h.item()),
                           "steps": len(e2e_ms), "warmup": 2,
                           "path": "per rank: vi_points_reserve + vi_points_add(host pinned shard) + vi_build(fast, sharded) + vi_ranges_copy"},
-                  "cpu_baseline": None}
+                  "search": search, "cpu_baseline": None}
         log(f"[{world} GPUs] build {ms_per_step:.2f} ms/step, e2e {e2e:.1f} ms/step; rank0 levels: "
             + str([(l.level, l.ranges, l.points, round(l.stats_ms, 2), round(l.partition_ms, 2)) for l in levels]))
-        print(json.dumps(result), flush=True)
+        emit(result)
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -292,6 +350,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
@@ -306,7 +365,7 @@ def main():
     if world > 1:
         return run_multi(args, rank, world, local)
     if args.gpus > 1:
-        print(json.dumps({"error": "launch N>1 with torch.distributed.run (one process per GPU)", "n_gpus": args.gpus}))
+        emit({"error": "launch N>1 with torch.distributed.run (one process per GPU)", "n_gpus": args.gpus})
         return
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -418,7 +477,7 @@ def main():
         del q_d, offs_d
 
     if args.no_e2e:
-        print(json.dumps(result), flush=True)
+        emit(result)
         return
     # ---- e2e: host buffers through the C ABI ---------------------------------------------------------------------
     rows_h = torch.empty((n, DIMS), dtype=torch.float32, pin_memory=True)
@@ -468,7 +527,7 @@ def main():
         cb, _ = cpu_baseline(rows_np, ids_np, args.cpu_sample_rows)
         result["cpu_baseline"] = cb
         log(f"cpu baseline: {cb['value']:.0f} vectors/s ({cb['sample']})")
-    print(json.dumps(result), flush=True)
+    emit(result)
 
 
 if __name__ == "__main__":

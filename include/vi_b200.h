@@ -142,8 +142,15 @@ typedef int (*vi_alltoallv_fn)(void* user, const void* d_send, const int64_t* se
                                const int64_t* recv_bytes);
 int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64_fn allreduce,
                       vi_alltoallv_fn alltoallv, void* user);
-/* Rows [0, *shared_rows) of this context's table are the replicated top levels; the rest belong to its sub-trees. */
+/* Rows [0, *shared_rows) of this context's table were numbered while the ranges were shared: the rows of levels < L
+ * are identical on every rank; a level-L range's row is filled in by the rank that owns the range and is a placeholder
+ * with Dimension == -2 on the others.  Rows from *shared_rows on belong to the sub-trees this rank owns. */
 int vi_shared_rows(const vi_ctx* ctx, int64_t* shared_rows);
+/* After a multi-rank build: gathers every rank's rows so that each context holds the WHOLE range table (row links
+ * remapped) and can answer any query -- "search shards the query batch against a replicated range table".  One
+ * all-reduce of 32 bytes per row.  Collective: every rank must call it.  The vectors stay with their owners, so
+ * vi_search_verify is not available on a replicated table. */
+int vi_table_replicate(vi_ctx* ctx);
 
 /* ---- utilities -------------------------------------------------------------------------------------------------- */
 /* Raw device pointers of the built table for zero-copy consumers (valid until the next build/reserve/destroy). */

@@ -40,8 +40,14 @@ def _worker(rank, world, port, q, n, d, seed, kind):
     info = ctx.build(vi.MODE_FAST)
     rid, dim, mid, oid = ctx.ranges()
     shared = ctx.shared_rows
-    # p = 0 lookups of owned points against the local part of the table are not meaningful across ranks; only rows
-    q.put((rank, rid, dim, mid.view(np.uint32), oid, shared, dict(coll.calls), int(info.levels)))
+    calls = dict(coll.calls)
+    # replicate: every rank must now hold the whole table and answer any query like the oracle
+    ctx.replicate()
+    frid, fdim, fmid, foid = ctx.ranges()
+    queries = np.concatenate([rows[: 40], rows[n - 40:]], 0)
+    offs, out = ctx.search(queries, 0.02)
+    q.put((rank, rid, dim, mid.view(np.uint32), oid, shared, calls, int(info.levels),
+           (frid, fdim, fmid.view(np.uint32), foid, offs, out)))
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
@@ -70,11 +76,13 @@ def test_sharded_build_equals_oracle(world, n, d, seed, kind):
     union = {}
     owned_rows = []
     for r in range(world):
-        rid, dim, mid, oid, shared, calls, levels = res[r]
+        rid, dim, mid, oid, shared, calls, levels, full = res[r]
         assert calls["alltoallv"] == 2  # rows + ids, once
         for k in range(len(rid)):
             val = (int(dim[k]), int(mid[k]), int(oid[k]))
             if k < shared:
+                if dim[k] == -2:
+                    continue  # root row of a range owned by another rank (placeholder)
                 assert union.setdefault(int(rid[k]), val) == val  # replicated top rows agree
             else:
                 assert int(rid[k]) not in union
@@ -87,6 +95,16 @@ def test_sharded_build_equals_oracle(world, n, d, seed, kind):
             for r, dm, m, i in zip(ref.range_id, ref.dimension, ref.mid, ref.id)}
     assert union == want
     assert sum(owned_rows) + res[0][4] == len(want)
+    # replicated tables: identical content on every rank, searches equal the oracle's
+    queries = np.concatenate([rows[: 40], rows[n - 40:]], 0)
+    roffs, rout, _ = oracle.search(ref, queries, 0.02)
+    for r in range(world):
+        frid, fdim, fmid, foid, offs, out = res[r][7]
+        got = {int(a): (int(b), int(c), int(e)) for a, b, c, e in zip(frid, fdim, fmid, foid)}
+        assert got == want
+        assert np.array_equal(offs, roffs)
+        for i in range(len(queries)):
+            assert sorted(out[offs[i]:offs[i + 1]].tolist()) == sorted(rout[roffs[i]:roffs[i + 1]].tolist())
     if kind == "unit_gaussian":
         # ownership is balanced: no rank owns more than 1.5x its fair share of the rows
         assert max(owned_rows) <= 1.5 * len(want) / world

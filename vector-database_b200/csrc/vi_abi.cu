@@ -69,7 +69,7 @@ void vi_destroy(vi_ctx* ctx)
   free_points(ctx);
   cudaFree(ctx->q_buf); cudaFree(ctx->off_buf); cudaFree(ctx->ids_buf); cudaFree(ctx->off2_buf);
   cudaFree(ctx->ids2_buf); cudaFree(ctx->search_src); cudaFree(ctx->verify_keep);
-  cudaFree(ctx->own_rows); cudaFree(ctx->own_ids);
+  cudaFree(ctx->own_rows); cudaFree(ctx->own_ids); cudaFree(ctx->send_rows); cudaFree(ctx->send_ids);
   cudaFree(ctx->counters);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -107,11 +107,17 @@ int vi_points_reserve(vi_ctx* ctx, int64_t capacity, int32_t dims)
   if (capacity < 0 || dims <= 0 || dims > 32767)  // `short dimensions`, FileRangeStore.cs:18
     return ctx->fail(VI_ERR_INVALID_ARG, "Invalid capacity or dimensions.");
   VI_CUDA_TRY(cudaSetDevice(ctx->device));
-  free_points(ctx);
-  vi_free_table(ctx);
-  vi_free_workspace(ctx);
-  ctx->dims = dims;
-  ctx->ld = (dims + 3) & ~3;
+  ctx->built = false;
+  if (dims != ctx->dims)
+  {
+    // buffers are sized per dimension count: start over
+    free_points(ctx);
+    vi_free_table(ctx);
+    vi_free_workspace(ctx);
+    ctx->dims = dims;
+    ctx->ld = (dims + 3) & ~3;
+  }
+  ctx->n = 0;  // drop the points; device buffers (points, work space, table) are kept and reused when large enough
   if (capacity == 0) return VI_OK;
   return reserve_points(ctx, capacity);
 }
@@ -308,6 +314,7 @@ int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims
   int64_t cand = 0;
   int* keep_src = ctx->search_src;
   ctx->search_src = nullptr;
+  if (ctx->replicated) return ctx->fail(VI_ERR_STATE, "candidate verification needs the vectors: not on a replicated table");
   rc = vi_search_impl(ctx, ctx->q_buf, nq, proximity, ctx->off_buf, nullptr, 0, &cand, nullptr, false);
   ctx->search_src = keep_src;
   if (rc != VI_OK) return rc;
@@ -348,6 +355,14 @@ int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64
   ctx->alltoallv = alltoallv;
   ctx->coll_user = user;
   return VI_OK;
+}
+
+int vi_table_replicate(vi_ctx* ctx)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  return vi_table_replicate_impl(ctx);
 }
 
 int vi_shared_rows(const vi_ctx* ctx, int64_t* shared_rows)

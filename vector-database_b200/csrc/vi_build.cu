@@ -674,7 +674,8 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
   cudaEvent_t ev_begin = env_event(ctx, env);
 
   // ---- global size and quantisation exponent ----------------------------------------------------------------
-  int rc = alloc_workspace(ctx, std::max<int64_t>(ctx->n, 1024));
+  // 25 % slack: the points a rank owns after the exchange are rarely exactly its shard size
+  int rc = alloc_workspace(ctx, std::max<int64_t>(ctx->n + ctx->n / 4, 4096));
   if (rc != VI_OK) return rc;
   float amax = 0.f;
   rc = local_absmax(ctx, ctx->rows, ctx->n, env, &amax);
@@ -880,8 +881,6 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
 
   // ---- phase B: ownership exchange --------------------------------------------------------------------------
   const u32 RL = (u32)segs.size();
-  cudaFree(ctx->own_rows); ctx->own_rows = nullptr;
-  cudaFree(ctx->own_ids); ctx->own_ids = nullptr;
   ctx->own_n = 0;
   LevelState s{};
   s.row_next = T;
@@ -906,6 +905,14 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
       owner[i] = (u32)best;
       load[best] += segs[i].gcount;
     }
+    // root rows of ranges owned elsewhere are placeholders here: Dimension -2
+    for (u32 i = 0; i < RL; ++i)
+      if (owner[i] != (u32)me)
+      {
+        const int dimv = -2;
+        VI_CUDA_TRY(cudaMemcpyAsync(ctx->t_dim + segs[i].row, &dimv, 4, cudaMemcpyHostToDevice, st));
+        VI_CUDA_TRY(cudaStreamSynchronize(st));
+      }
     // send layout: by destination rank, then range index, then local position
     std::vector<u32> send_base(RL, 0);
     std::vector<int64_t> send_rows_n(G, 0), recv_rows_n(G, 0);
@@ -926,18 +933,27 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
           recv_rows_n[g] += (int64_t)mat[(size_t)g * RL + i];
           nown += mat[(size_t)g * RL + i];
         }
-    float* send_rows = nullptr;
-    i64* send_ids = nullptr;
-    const size_t nsend = std::max<size_t>(nloc, 1), nrecv = std::max<size_t>((size_t)nown, 1);
-    VI_CUDA_TRY(cudaMalloc((void**)&send_rows, nsend * ld * sizeof(float)));
-    cudaError_t ce = cudaMalloc((void**)&send_ids, nsend * sizeof(i64));
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&ctx->own_rows, nrecv * ld * sizeof(float) + 256);
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&ctx->own_ids, nrecv * sizeof(i64) + 256);
-    if (ce != cudaSuccess)
+    // exchange buffers are kept across builds (cudaMalloc/cudaFree of GB-sized buffers costs milliseconds)
+    if ((int64_t)nloc > ctx->send_cap)
     {
-      cudaFree(send_rows); cudaFree(send_ids);
-      return ctx->fail_cuda(ce, "cudaMalloc(exchange buffers)", __FILE__, __LINE__);
+      cudaFree(ctx->send_rows); cudaFree(ctx->send_ids);
+      ctx->send_rows = nullptr; ctx->send_ids = nullptr; ctx->send_cap = 0;
+      const size_t c = (size_t)nloc + 1024;
+      VI_CUDA_TRY(cudaMalloc((void**)&ctx->send_rows, c * ld * sizeof(float)));
+      VI_CUDA_TRY(cudaMalloc((void**)&ctx->send_ids, c * sizeof(i64)));
+      ctx->send_cap = (int64_t)c;
     }
+    if ((int64_t)nown > ctx->own_cap)
+    {
+      cudaFree(ctx->own_rows); cudaFree(ctx->own_ids);
+      ctx->own_rows = nullptr; ctx->own_ids = nullptr; ctx->own_cap = 0;
+      const size_t c = (size_t)nown + (size_t)nown / 8 + 1024;
+      VI_CUDA_TRY(cudaMalloc((void**)&ctx->own_rows, c * ld * sizeof(float)));
+      VI_CUDA_TRY(cudaMalloc((void**)&ctx->own_ids, c * sizeof(i64)));
+      ctx->own_cap = (int64_t)c;
+    }
+    float* send_rows = ctx->send_rows;
+    i64* send_ids = ctx->send_ids;
     u32 A = 0;
     for (u32 i = 0; i < RL; ++i) A += segs[i].lcount;
     if (A > 0)
@@ -960,8 +976,6 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
     int cerr = ctx->alltoallv(ctx->coll_user, send_rows, sb.data(), ctx->own_rows, rb.data());
     for (int g = 0; g < G; ++g) { sb[g] = send_rows_n[g] * 8; rb[g] = recv_rows_n[g] * 8; }
     if (cerr == 0) cerr = ctx->alltoallv(ctx->coll_user, send_ids, sb.data(), ctx->own_ids, rb.data());
-    cudaFree(send_rows);
-    cudaFree(send_ids);
     if (cerr != 0) return ctx->fail(VI_ERR_CUDA, "all-to-all callback failed");
     ctx->own_n = (int64_t)nown;
 
@@ -1034,8 +1048,56 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
   return finish_table(ctx, env, s.row_next, ev_begin);
 }
 
+// Replicates the table of a multi-rank build on every rank (for query-sharded search).
+int vi_table_replicate_impl(vi_ctx* ctx)
+{
+  if (ctx->world <= 1 || ctx->replicated) return VI_OK;
+  cudaStream_t st = ctx->stream;
+  const int G = ctx->world, me = ctx->rank;
+  const u32 T = (u32)ctx->shared_rows, rows = (u32)ctx->t_rows;
+  std::vector<u64> own((size_t)G, 0);
+  own[me] = rows - T;
+  int rc = allreduce_host(ctx, own);
+  if (rc != VI_OK) return rc;
+  u64 total = T, my_off = T;
+  for (int g = 0; g < G; ++g)
+  {
+    if (g < me) my_off += own[g];
+    total += own[g];
+  }
+  if (total >= 0x7fffffffull) return ctx->fail(VI_ERR_CAPACITY, "replicated table too large for 32-bit row indexes");
+  u64* buf = nullptr;
+  VI_CUDA_TRY(cudaMalloc((void**)&buf, (size_t)total * 32 + 256));
+  cudaError_t e = cudaMemsetAsync(buf, 0, (size_t)total * 32, st);
+  if (e == cudaSuccess && rows > 0)
+    k_pack_table<<<(rows + 255) / 256, 256, 0, st>>>(ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high,
+                                                     rows, T, (u32)my_off, me == 0 ? 1 : 0, buf);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaFree(buf); return ctx->fail_cuda(e, "pack table", __FILE__, __LINE__); }
+  if (ctx->allreduce(ctx->coll_user, buf, (int64_t)total * 4) != 0)
+  {
+    cudaFree(buf);
+    return ctx->fail(VI_ERR_CUDA, "all-reduce callback failed");
+  }
+  rc = grow_table(ctx, (int64_t)total + 1024, 0);
+  if (rc != VI_OK) { cudaFree(buf); return rc; }
+  k_unpack_table<<<((u32)total + 255) / 256, 256, 0, st>>>(buf, (u32)total, ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id,
+                                                           ctx->t_low, ctx->t_high, ctx->t_src);
+  k_pack_nodes<<<((u32)total + 255) / 256, 256, 0, st>>>(ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high,
+                                                         ctx->t_node, (u32)total);
+  e = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  if (e != cudaSuccess) return ctx->fail_cuda(e, "unpack table", __FILE__, __LINE__);
+  ctx->t_rows = (int64_t)total;
+  ctx->shared_rows = (int64_t)total;
+  ctx->replicated = true;
+  ctx->info.ranges = (int64_t)total;
+  return VI_OK;
+}
+
 int vi_build_impl(vi_ctx* ctx, int mode)
 {
+  ctx->replicated = false;
   const int64_t n64 = ctx->n;
   ctx->built = false;
   ctx->shared_rows = 0;
@@ -1049,7 +1111,7 @@ int vi_build_impl(vi_ctx* ctx, int mode)
   if (ctx->world > 1)
   {
     // sized for the local shard; grown once the rank knows how many points it owns (build_sharded phase C)
-    rc = alloc_table(ctx, std::max<int64_t>(n64, 4096));
+    rc = alloc_table(ctx, std::max<int64_t>(n64 + n64 / 4, 4096));
     if (rc == VI_OK) rc = build_sharded(ctx, env);
   }
   else if (n64 == 0)

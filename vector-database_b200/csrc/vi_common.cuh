@@ -119,9 +119,13 @@ struct vi_ctx
   vi_alltoallv_fn alltoallv = nullptr;
   void* coll_user = nullptr;
   int64_t shared_rows = 0;      // rows of the replicated top levels (multi-rank build), else 0
+  bool replicated = false;      // vi_table_replicate done: every rank holds the whole table
   float* own_rows = nullptr;    // multi-rank build: rows / ids of the ranges this rank owns (replace rows/ids as the
   i64* own_ids = nullptr;       // data the table's t_src refers to)
-  int64_t own_n = 0;
+  int64_t own_n = 0, own_cap = 0;
+  float* send_rows = nullptr;   // all-to-all send buffers (kept across builds)
+  i64* send_ids = nullptr;
+  int64_t send_cap = 0;
 
   int fail(int code, const std::string& msg)
   {
@@ -172,6 +176,7 @@ __device__ __forceinline__ u32 hi_before(const u32* __restrict__ wpre, const u32
 }
 
 // build entry points implemented in vi_build.cu / vi_search.cu
+int vi_table_replicate_impl(vi_ctx* ctx);
 int vi_debug_divcheck_impl(vi_ctx* ctx, uint64_t seed, int64_t samples, int64_t* mismatches);
 int vi_build_impl(vi_ctx* ctx, int mode);
 int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proximity, i64* d_offsets, i64* d_ids,

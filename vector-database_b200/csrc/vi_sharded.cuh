@@ -92,3 +92,51 @@ k_forest_init(u32 A, u32 npieces, const u32* __restrict__ piece_dst, const u32* 
   pid[p] = ids[r];
   seg_of[p] = piece_seg[lo];
 }
+
+// ---- table replication (query-sharded search against a replicated table) ---------------------------------------
+// Every row becomes 4 u64 words [rid][dim | mid][id][low | high]; a rank writes the rows it is responsible for into
+// its slice of a zero-filled buffer (links already remapped to global row indexes), one sum-all-reduce concatenates.
+__global__ void __launch_bounds__(256)
+k_pack_table(const i64* __restrict__ t_rid, const int* __restrict__ t_dim, const float* __restrict__ t_mid,
+             const i64* __restrict__ t_id, const int* __restrict__ t_low, const int* __restrict__ t_high, u32 rows,
+             u32 shared, u32 own_offset, int contribute_shared, u64* __restrict__ out)
+{
+  const u32 i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= rows) return;
+  const int dim = t_dim[i];
+  u32 g;  // global row index
+  if (i < shared)
+  {
+    // replicated rows come from rank 0 only; a level-L root row comes from its owner (placeholders have dim -2)
+    const bool root_owned = t_low[i] >= (int)shared || t_high[i] >= (int)shared;
+    if (dim == -2 || (!contribute_shared && !root_owned)) return;
+    g = i;
+  }
+  else
+    g = own_offset + (i - shared);
+  int lo = t_low[i], hi = t_high[i];
+  if (lo >= (int)shared) lo = (int)(own_offset + ((u32)lo - shared));
+  if (hi >= (int)shared) hi = (int)(own_offset + ((u32)hi - shared));
+  u64* o = out + (size_t)g * 4;
+  o[0] = (u64)t_rid[i];
+  o[1] = ((u64)(u32)__float_as_int(t_mid[i]) << 32) | (u64)(u32)dim;
+  o[2] = (u64)t_id[i];
+  o[3] = ((u64)(u32)hi << 32) | (u64)(u32)lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack_table(const u64* __restrict__ in, u32 rows, i64* __restrict__ t_rid, int* __restrict__ t_dim,
+               float* __restrict__ t_mid, i64* __restrict__ t_id, int* __restrict__ t_low, int* __restrict__ t_high,
+               int* __restrict__ t_src)
+{
+  const u32 i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= rows) return;
+  const u64* o = in + (size_t)i * 4;
+  t_rid[i] = (i64)o[0];
+  t_dim[i] = (int)(u32)o[1];
+  t_mid[i] = __int_as_float((int)(u32)(o[1] >> 32));
+  t_id[i] = (i64)o[2];
+  t_low[i] = (int)(u32)o[3];
+  t_high[i] = (int)(u32)(o[3] >> 32);
+  t_src[i] = -1;  // the vectors stay with their owners: no candidate verification on a replicated table
+}

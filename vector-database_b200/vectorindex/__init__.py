@@ -54,7 +54,7 @@ ALLTOALLV_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 EXPORTS = ["vi_abi_version", "vi_create", "vi_destroy", "vi_last_error", "vi_points_reserve", "vi_points_add",
            "vi_points_add_device", "vi_points_count", "vi_build", "vi_build_levels", "vi_range_count",
            "vi_ranges_copy", "vi_textindex_copy", "vi_search", "vi_search_device", "vi_search_verify",
-           "vi_set_collective", "vi_shared_rows", "vi_table_device", "vi_stream", "vi_debug_divcheck"]
+           "vi_set_collective", "vi_shared_rows", "vi_table_replicate", "vi_table_device", "vi_stream", "vi_debug_divcheck"]
 
 _lib = None
 
@@ -94,6 +94,7 @@ def load_library() -> ctypes.CDLL:
                                    _i64p, ctypes.c_int64, _i64p]
     L.vi_set_collective.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ALLREDUCE_FN, ALLTOALLV_FN, vp]
     L.vi_shared_rows.argtypes = [vp, _i64p]
+    L.vi_table_replicate.argtypes = [vp]
     L.vi_table_device.argtypes = [vp] + [ctypes.POINTER(vp)] * 6
     L.vi_stream.argtypes = [vp]
     L.vi_debug_divcheck.argtypes = [vp, ctypes.c_uint64, ctypes.c_int64, _i64p]
@@ -298,6 +299,10 @@ class Context:
 
         self._cb = (ALLREDUCE_FN(_ar), ALLTOALLV_FN(_a2a))  # keep the thunks alive
         self._check(self._L.vi_set_collective(self._h, rank, world, self._cb[0], self._cb[1], None))
+
+    def replicate(self) -> None:
+        """multi-rank: every rank gets the whole table (collective call)"""
+        self._check(self._L.vi_table_replicate(self._h))
 
     @property
     def shared_rows(self) -> int:
