@@ -57,6 +57,8 @@ typedef struct vi_build_info
   double build_ms;       /* device time of the whole build, CUDA events */
   int32_t q_exponent;    /* fast mode: E with max|x| < 2^E */
   int32_t reserved;
+  double subtree_ms;     /* fast mode: device time of the sub-tree kernel (ranges of <= 32 points, vi_subtree.cuh) */
+  int64_t subtree_ranges;/* ranges handed to it */
 } vi_build_info;
 
 /* Per-level record (profiling / roofline accounting, Program.cs has only a whole-build Stopwatch). */
@@ -66,8 +68,9 @@ typedef struct vi_level_info
   int32_t reserved;
   int64_t ranges;        /* non-leaf ranges processed at this level */
   int64_t points;        /* points in them (A_l) */
-  int64_t rows_emitted;  /* table rows of this level (leaves included) */
-  double stats_ms, partition_ms;
+  int64_t rows_emitted;  /* table rows created by this level's partition pass */
+  double stats_ms, partition_ms; /* level-synchronous passes only; sub-tree kernel time is vi_build_info.subtree_ms */
+  int64_t in_subtrees;   /* of `points`, those processed inside the sub-tree kernel */
 } vi_level_info;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */
@@ -99,7 +102,9 @@ int vi_build_levels(const vi_ctx* ctx, vi_level_info* out, int32_t cap, int32_t*
 
 /* ---- range table out: the (rangeId, RangeValue) stream of Build (IndexBuilder.cs:92, RangeValue.cs) ---------- */
 int64_t vi_range_count(const vi_ctx* ctx);
-/* Rows in breadth-first order, ascending rangeId inside a level.  Any output pointer may be NULL.
+/* One row per non-empty range, keyed by RangeID (row order is unspecified: the level-synchronous part comes
+ * breadth-first, sub-trees finished by the sub-tree kernel come as dense depth-first blocks; the reference's
+ * consumers key rows by rangeId, Program.cs:18-26).  Any output pointer may be NULL.
  * dimension == -1 marks a leaf (RangeValue.Dimension), id is the leaf's point id there and the tie-break pivot
  * elsewhere (RangeValue.Id). */
 int vi_ranges_copy(const vi_ctx* ctx, int64_t* range_id, int32_t* dimension, float* mid, int64_t* id, int64_t cap);

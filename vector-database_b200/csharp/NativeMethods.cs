@@ -17,7 +17,7 @@ internal static partial class NativeMethods
   public struct BuildInfo
   {
     public long ranges; public int levels; public int mode; public long pointVisits; public long kernelLaunches;
-    public double buildMs; public int qExponent; public int reserved;
+    public double buildMs; public int qExponent; public int reserved; public double subtreeMs; public long subtreeRanges;
   }
 
   [LibraryImport(Lib)] public static partial int vi_abi_version();

@@ -19,6 +19,7 @@
 #include "vi_sharded.cuh"
 #include "vi_stats_exact.cuh"
 #include "vi_stats_fast.cuh"
+#include "vi_subtree.cuh"
 
 // =============================================================================================================
 // level 0 set-up
@@ -106,6 +107,15 @@ void vi_free_workspace(vi_ctx* ctx)
   cudaFree(ctx->c_rows); ctx->c_rows = nullptr;
   cudaFree(ctx->c_actpos); ctx->c_actpos = nullptr;
   cudaFree(ctx->scan_tmp); ctx->scan_tmp = nullptr;
+  cudaFree(ctx->c_sub); ctx->c_sub = nullptr;
+  cudaFree(ctx->sub_perm); ctx->sub_perm = nullptr;
+  cudaFree(ctx->sub_pid); ctx->sub_pid = nullptr;
+  cudaFree(ctx->sub_start); ctx->sub_start = nullptr;
+  cudaFree(ctx->sub_count); ctx->sub_count = nullptr;
+  cudaFree(ctx->sub_rid); ctx->sub_rid = nullptr;
+  cudaFree(ctx->sub_row); ctx->sub_row = nullptr;
+  cudaFree(ctx->sub_depth); ctx->sub_depth = nullptr;
+  cudaFree(ctx->sub_stats); ctx->sub_stats = nullptr;
   cudaFree(ctx->gacc); ctx->gacc = nullptr;
   cudaFree(ctx->gstats); ctx->gstats = nullptr;
   cudaFree(ctx->d_absmax); ctx->d_absmax = nullptr;
@@ -160,6 +170,15 @@ static int alloc_workspace(vi_ctx* ctx, int64_t n)
   VI_CUDA_TRY(dalloc(&ctx->seg_hbase, maxseg));
   VI_CUDA_TRY(dalloc(&ctx->c_rows, maxseg + 1));
   VI_CUDA_TRY(dalloc(&ctx->c_actpos, maxseg + 1));
+  VI_CUDA_TRY(dalloc(&ctx->c_sub, maxseg + 1));
+  VI_CUDA_TRY(dalloc(&ctx->sub_perm, N));
+  VI_CUDA_TRY(dalloc(&ctx->sub_pid, N));
+  VI_CUDA_TRY(dalloc(&ctx->sub_start, maxseg));
+  VI_CUDA_TRY(dalloc(&ctx->sub_count, maxseg));
+  VI_CUDA_TRY(dalloc(&ctx->sub_rid, maxseg));
+  VI_CUDA_TRY(dalloc(&ctx->sub_row, maxseg));
+  VI_CUDA_TRY(dalloc(&ctx->sub_depth, maxseg));
+  VI_CUDA_TRY(dalloc(&ctx->sub_stats, (size_t)160));
   VI_CUDA_TRY(dalloc((u64**)&ctx->scan_tmp, maxseg / SCAN_TILE + words / SCAN_TILE + 64));
   VI_CUDA_TRY(dalloc(&ctx->gacc, maxbig * ((size_t)ctx->ld * 3 + 3)));
   VI_CUDA_TRY(dalloc(&ctx->gstats, maxbig * (size_t)ctx->dims));
@@ -305,6 +324,8 @@ struct BuildEnv
 {
   int mode;
   u32 t_team, t_big, big_unroll;
+  u32 t_sub;  // ranges of 2..t_sub points are finished by the sub-tree kernel (0 = off)
+  u32 sub_minb;
   FastShape shp;
   int chx;
   float qk;
@@ -318,6 +339,7 @@ struct LevelState
 {
   u32 A, R, nbig, chunks, minseg, maxseg;
   u32 row_next;  // first free table row
+  u32 sub_cnt, sub_pos;  // sub-tree list: entries and points so far
   int cur;       // ping-pong index of the current level's buffers
   int level;     // depth of the ranges in seg[cur]
 };
@@ -347,6 +369,11 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   const u32 t_big_exact = env_u32("VI_B200_T_BIG_EXACT", 512, VI_MIN_BIG, 1u << 30);
   env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
   env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 4, 1, 4);
+  // sub-tree kernel (fast mode): as many rows as fit 12 KB of shared memory per warp, at most 32 (one point per lane)
+  u32 sub_rows = std::min<u32>(32u, (u32)(12288 / (ctx->ld * 4)));
+  if (sub_rows < 4 || mode != VI_MODE_FAST || ctx->ld > 128) sub_rows = 0;  // wider rows stay on the level path
+  env.t_sub = std::min(env_u32("VI_B200_T_SUB", sub_rows, 0, 32), sub_rows);
+  env.sub_minb = env_u32("VI_B200_SUB_MINB", 2, 2, 3);
   env.shp = fast_shape(ctx->ld);
   env.chx = exact_chx(ctx->dims);
   env.qk = 1.0f;
@@ -402,6 +429,98 @@ static void launch_big_fast(vi_ctx* ctx, BuildEnv& env, const float* rows, int c
   FAST_DISPATCH(env.shp, CALL_BIG);
 #undef CALL_BIG
   ++env.launches;
+}
+
+// Finishes every range on the sub-tree list (vi_subtree.cuh); advances s.row_next past their rows.
+static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* rows)
+{
+  if (s.sub_cnt == 0) return VI_OK;
+  cudaStream_t st = ctx->stream;
+  const int ld = ctx->ld, dims = ctx->dims;
+  const int rows_max = (int)env.t_sub;
+  const u32 row_base = s.row_next;
+  const u32 overflow_base = row_base + 2u * s.sub_pos - 2u * s.sub_cnt;
+  unsigned long long* lvlp = (unsigned long long*)ctx->sub_stats;  // [64] points, [64] ranges, then 2 u32 counters
+  unsigned long long* lvlr = lvlp + 64;
+  u32* cnt = (u32*)(lvlr + 64);
+  VI_CUDA_TRY(cudaMemsetAsync(ctx->sub_stats, 0, 160 * 8, st));
+  TableOut tout{ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high};
+  SubList sl{ctx->sub_start, ctx->sub_count, ctx->sub_rid, ctx->sub_row, ctx->sub_depth};
+  const size_t smem = (size_t)SUB_WARPS * rows_max * ld * sizeof(float);
+  const u32 grid = std::min<u32>((s.sub_cnt + SUB_WARPS - 1) / SUB_WARPS, (u32)VI_NUM_SMS * 8 * env.sub_minb);
+  cudaEvent_t e0 = env_event(ctx, env);
+#define CALL_SUB2(CH, MINB)                                                                                                 \
+  do                                                                                                                        \
+  {                                                                                                                         \
+    if (sub_full)                                                                                                           \
+    {                                                                                                                       \
+      VI_CUDA_TRY(cudaFuncSetAttribute(k_subtree_fast<CH, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                       (int)smem));                                                                         \
+      k_subtree_fast<CH, MINB, true><<<grid, SUB_WARPS * 32, smem, st>>>(                                                   \
+          sl, s.sub_cnt, ctx->sub_perm, ctx->sub_pid, rows, ld, dims, env.qk, env.qinv, tout, ctx->t_src, row_base,         \
+          overflow_base, (u32)ctx->t_cap, cnt, lvlp, lvlr, rows_max);                                                       \
+    }                                                                                                                       \
+    else                                                                                                                    \
+    {                                                                                                                       \
+      VI_CUDA_TRY(cudaFuncSetAttribute(k_subtree_fast<CH, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                       (int)smem));                                                                         \
+      k_subtree_fast<CH, MINB, false><<<grid, SUB_WARPS * 32, smem, st>>>(                                                  \
+          sl, s.sub_cnt, ctx->sub_perm, ctx->sub_pid, rows, ld, dims, env.qk, env.qinv, tout, ctx->t_src, row_base,         \
+          overflow_base, (u32)ctx->t_cap, cnt, lvlp, lvlr, rows_max);                                                       \
+    }                                                                                                                       \
+  } while (0)
+#define CALL_SUB(CH)                                  \
+  do                                                  \
+  {                                                   \
+    if (env.sub_minb >= 3) CALL_SUB2(CH, 3);          \
+    else CALL_SUB2(CH, 2);                            \
+  } while (0)
+  const bool sub_full = (ld % 32 == 0) && dims == ld;
+  const int ch = (ld / 4 + 7) / 8;  // float4 chunks per team lane (rows up to 128 floats wide, see env_init)
+  if (ch <= 1) CALL_SUB(1);
+  else if (ch == 2) CALL_SUB(2);
+  else if (ch == 3) CALL_SUB(3);
+  else CALL_SUB(4);
+#undef CALL_SUB2
+#undef CALL_SUB
+  ++env.launches;
+  cudaEvent_t e1 = env_event(ctx, env);
+  unsigned long long h[130];
+  VI_CUDA_TRY(cudaMemcpyAsync(h, ctx->sub_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaStreamSynchronize(st));
+  VI_CUDA_TRY(cudaGetLastError());
+  const u32 overflow = (u32)(h[128] & 0xffffffffu), err = (u32)(h[128] >> 32);
+  if (err == 1) return ctx->fail(VI_ERR_CAPACITY, "range table capacity exceeded (degenerate input: too many one-child ranges)");
+  if (err == 2)
+    return ctx->fail(VI_ERR_OVERFLOW, "rangeId overflow: a range at depth 62 still holds more than one point "
+                                      "(IndexBuilder.cs:99 checked(rangeId * 2 + 1))");
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ctx->info.subtree_ms += ms;
+  ctx->info.subtree_ranges += s.sub_cnt;
+  // per-depth accounting: the sub-trees' ranges belong to levels like everyone else's
+  for (int d = 0; d < 64; ++d)
+  {
+    if (!h[d] && !h[64 + d]) continue;
+    vi_level_info* li = nullptr;
+    for (auto& l : ctx->levels)
+      if (l.level == d) li = &l;
+    if (!li)
+    {
+      vi_level_info n{};
+      n.level = d;
+      ctx->levels.push_back(n);
+      li = &ctx->levels.back();
+    }
+    li->points += (int64_t)h[d];
+    li->ranges += (int64_t)h[64 + d];
+    li->in_subtrees += (int64_t)h[d];
+    ctx->info.point_visits += (int64_t)h[d];
+  }
+  s.row_next = overflow_base + overflow;
+  s.sub_cnt = 0;
+  s.sub_pos = 0;
+  return VI_OK;
 }
 
 // The level loop: processes seg[s.cur] (ranges of depth s.level) until no range with >= 2 points is left.
@@ -503,10 +622,12 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
     ++env.launches;
     scan_exclusive<u32>(ctx, ctx->wpre, W + 1, env.launches);
     k_seg_children<<<(R + 255) / 256, 256, 0, st>>>(sg, R, ctx->wpre, ctx->fbits, ctx->seg_nlo, ctx->seg_hbase,
-                                                    ctx->c_rows, ctx->c_actpos);
+                                                    ctx->c_rows, ctx->c_actpos, ctx->c_sub, env.t_sub);
     ++env.launches;
     scan_exclusive<u32>(ctx, ctx->c_rows, R, env.launches);
     scan_exclusive<u64>(ctx, ctx->c_actpos, R, env.launches);
+    if (env.t_sub) scan_exclusive<u64>(ctx, ctx->c_sub, R, env.launches);
+    else VI_CUDA_TRY(cudaMemsetAsync(ctx->c_sub, 0, ((size_t)R + 1) * 8, st));
     {
       const u32 init[8] = {0u, 0u, 0u, 0u, 0xffffffffu, 0u, 0u, 0u};  // [0] nbig [1] err [4] minseg [5] maxseg
       VI_CUDA_TRY(cudaMemcpyAsync(lvl_counters, init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -514,11 +635,14 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
     const u32 row_base_next = s.row_next;
     k_emit_children<<<(R + 255) / 256, 256, 0, st>>>(sg, R, ctx->seg_nlo, ctx->c_rows, ctx->c_actpos, ctx->seg[nxt],
                                                      row_base_next, (u32)ctx->t_cap, tout, ctx->big_list[nxt], t_big,
-                                                     lvl_counters);
+                                                     lvl_counters, ctx->c_sub, env.t_sub, s.sub_cnt, s.sub_pos,
+                                                     (u32)s.level + 1u, ctx->sub_start, ctx->sub_count, ctx->sub_rid,
+                                                     ctx->sub_row, ctx->sub_depth);
     k_scatter<<<(A + 255) / 256, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], A, ctx->fbits,
                                                ctx->wpre, ctx->seg_nlo, ctx->seg_hbase, ctx->c_rows, ctx->c_actpos,
                                                row_base_next, ctx->perm[nxt], ctx->pid[nxt], ctx->seg_of[nxt], ctx->t_id,
-                                               ctx->t_src, lvl_counters);
+                                               ctx->t_src, lvl_counters, ctx->c_sub, env.t_sub, s.sub_pos, ctx->sub_perm,
+                                               ctx->sub_pid);
     env.launches += 2;
     const u32 big_bound = A / t_big + 1;
     u32* chunk_arr = nullptr;
@@ -530,7 +654,7 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
       ++env.launches;
       scan_exclusive<u32>(ctx, chunk_arr, big_bound, env.launches);
     }
-    k_totals<<<1, 1, 0, st>>>(ctx->c_rows, ctx->c_actpos, R, lvl_counters, chunk_arr, big_bound, ctx->totals);
+    k_totals<<<1, 1, 0, st>>>(ctx->c_rows, ctx->c_actpos, ctx->c_sub, R, lvl_counters, chunk_arr, big_bound, ctx->totals);
     ++env.launches;
     cudaEvent_t e2 = env_event(ctx, env);
     VI_CUDA_TRY(cudaStreamSynchronize(st));
@@ -557,10 +681,12 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
     s.chunks = tt.chunks;
     s.minseg = tt.minseg;
     s.maxseg = tt.maxseg;
+    s.sub_cnt += tt.subs;
+    s.sub_pos += tt.subpos;
     s.cur = nxt;
     ++s.level;
   }
-  return VI_OK;
+  return run_subtrees(ctx, env, s, rows);
 }
 
 static int finish_table(vi_ctx* ctx, BuildEnv& env, u32 total_rows, cudaEvent_t ev_begin)
@@ -577,6 +703,8 @@ static int finish_table(vi_ctx* ctx, BuildEnv& env, u32 total_rows, cudaEvent_t 
   VI_CUDA_TRY(cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, ev_begin, ev_end);
+  std::stable_sort(ctx->levels.begin(), ctx->levels.end(),
+                   [](const vi_level_info& a, const vi_level_info& b) { return a.level < b.level; });
   ctx->t_rows = total_rows;
   ctx->built = true;
   ctx->info.ranges = total_rows;
@@ -776,7 +904,7 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
       ++env.launches;
       scan_exclusive<u32>(ctx, ctx->wpre, W + 1, env.launches);
       k_seg_children<<<(R + 255) / 256, 256, 0, st>>>(sg, R, ctx->wpre, ctx->fbits, ctx->seg_nlo, ctx->seg_hbase,
-                                                      ctx->c_rows, ctx->c_actpos + 4096);
+                                                      ctx->c_rows, ctx->c_actpos + 4096, ctx->c_sub, 0u);
       ++env.launches;
       VI_CUDA_TRY(cudaMemcpyAsync(h_nlo.data(), ctx->seg_nlo, R * 4, cudaMemcpyDeviceToHost, st));
     }

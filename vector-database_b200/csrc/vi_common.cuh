@@ -51,6 +51,8 @@ struct LevelTotals  // pinned host, written by the device at the end of every le
   u32 err;       // range table capacity exceeded
   u32 minseg;    // smallest / largest next-level range
   u32 maxseg;
+  u32 subs;      // children handed to the sub-tree kernel this level, and their points
+  u32 subpos;
 };
 
 struct vi_ctx
@@ -81,6 +83,15 @@ struct vi_ctx
   u32* seg_hbase = nullptr;                 // per segment: hi flags before its first position
   u32* c_rows = nullptr;                    // per segment child row count (scanned in place, + total)
   u64* c_actpos = nullptr;                  // per segment (active children << 32 | active positions) (+ total)
+  u64* c_sub = nullptr;                     // per segment (sub-tree children << 32 | their points) (+ total)
+  u32* sub_perm = nullptr;                  // sub-tree position space: row index / id per point
+  i64* sub_pid = nullptr;
+  u32* sub_start = nullptr;                 // sub-tree list
+  u32* sub_count = nullptr;
+  i64* sub_rid = nullptr;
+  u32* sub_row = nullptr;
+  u32* sub_depth = nullptr;
+  u64* sub_stats = nullptr;                 // [64] points + [64] ranges per depth, then the kernel's 2 counters
   void* scan_tmp = nullptr;                 // block sums for scans
   u64* gacc = nullptr;                      // fast mode: per big slot [dims][4] + [2] id sums
   float2* gstats = nullptr;                 // exact mode: per big slot [dims] (mean, q)

@@ -34,7 +34,7 @@ k_flags(SegLevel sg, const u32* __restrict__ seg_of, const u32* __restrict__ per
 
 __global__ void __launch_bounds__(256)
 k_seg_children(SegLevel sg, u32 R, const u32* __restrict__ wpre, const u32* __restrict__ fbits, u32* seg_nlo,
-               u32* seg_hbase, u32* c_rows, u64* c_actpos)
+               u32* seg_hbase, u32* c_rows, u64* c_actpos, u64* c_sub, u32 t_sub)
 {
   const u32 s = blockIdx.x * 256u + threadIdx.x;
   if (s >= R) return;
@@ -45,9 +45,11 @@ k_seg_children(SegLevel sg, u32 R, const u32* __restrict__ wpre, const u32* __re
   seg_nlo[s] = nlo;
   seg_hbase[s] = hb;
   c_rows[s] = (nlo > 0) + (nhi > 0);
-  const u32 act = (nlo >= 2) + (nhi >= 2);
-  const u32 pos = (nlo >= 2 ? nlo : 0) + (nhi >= 2 ? nhi : 0);
-  c_actpos[s] = ((u64)act << 32) | (u64)pos;
+  // a child with one point is a leaf, with 2..t_sub points it goes to the sub-tree list, otherwise it stays a range
+  const bool lo_sub = nlo >= 2 && nlo <= t_sub, hi_sub = nhi >= 2 && nhi <= t_sub;
+  const bool lo_act = nlo > 1 && !lo_sub, hi_act = nhi > 1 && !hi_sub;
+  c_actpos[s] = ((u64)((u32)lo_act + (u32)hi_act) << 32) | (u64)((lo_act ? nlo : 0u) + (hi_act ? nhi : 0u));
+  c_sub[s] = ((u64)((u32)lo_sub + (u32)hi_sub) << 32) | (u64)((lo_sub ? nlo : 0u) + (hi_sub ? nhi : 0u));
 }
 
 struct TableOut
@@ -64,7 +66,9 @@ struct TableOut
 __global__ void __launch_bounds__(256)
 k_emit_children(SegLevel sg, u32 R, const u32* __restrict__ seg_nlo, const u32* __restrict__ c_rows,
                 const u64* __restrict__ c_actpos, SegLevel nx, u32 row_base_next, u32 t_cap, TableOut t,
-                u32* big_list_next, u32 big_thr, u32* counters)
+                u32* big_list_next, u32 big_thr, u32* counters, const u64* __restrict__ c_sub, u32 t_sub,
+                u32 sub_cnt_base, u32 sub_pos_base, u32 child_depth, u32* sub_start, u32* sub_count, i64* sub_rid,
+                u32* sub_row, u32* sub_depth)
 {
   const u32 s = blockIdx.x * 256u + threadIdx.x;
   if ((u64)row_base_next + c_rows[R] > (u64)t_cap)
@@ -80,6 +84,9 @@ k_emit_children(SegLevel sg, u32 R, const u32* __restrict__ seg_nlo, const u32* 
     const u32 row = sg.row[s];
     const u32 r0 = row_base_next + c_rows[s];
     const u32 a0 = (u32)(c_actpos[s] >> 32), p0 = (u32)c_actpos[s];
+    const u32 b0 = sub_cnt_base + (u32)(c_sub[s] >> 32), q0 = sub_pos_base + (u32)c_sub[s];
+    const bool lo_sub = nlo >= 2 && nlo <= t_sub, hi_sub = nhi >= 2 && nhi <= t_sub;
+    const bool lo_act = nlo > 1 && !lo_sub;
     const int lo_row = nlo > 0 ? (int)r0 : -1;
     const int hi_row = nhi > 0 ? (int)(r0 + (nlo > 0 ? 1u : 0u)) : -1;
     t.t_low[row] = lo_row;
@@ -93,6 +100,14 @@ k_emit_children(SegLevel sg, u32 R, const u32* __restrict__ seg_nlo, const u32* 
       {
         t.t_dim[lo_row] = -1;  // leaf, IndexBuilder.cs:81-82; its Id is written by k_scatter
         t.t_mid[lo_row] = 0.0f;
+      }
+      else if (lo_sub)
+      {
+        sub_start[b0] = q0;
+        sub_count[b0] = nlo;
+        sub_rid[b0] = rid * 2 + 1;
+        sub_row[b0] = (u32)lo_row;
+        sub_depth[b0] = child_depth;
       }
       else
       {
@@ -115,10 +130,19 @@ k_emit_children(SegLevel sg, u32 R, const u32* __restrict__ seg_nlo, const u32* 
         t.t_dim[hi_row] = -1;
         t.t_mid[hi_row] = 0.0f;
       }
+      else if (hi_sub)
+      {
+        const u32 b1 = b0 + (lo_sub ? 1u : 0u);
+        sub_start[b1] = q0 + (lo_sub ? nlo : 0u);
+        sub_count[b1] = nhi;
+        sub_rid[b1] = rid * 2 + 2;
+        sub_row[b1] = (u32)hi_row;
+        sub_depth[b1] = child_depth;
+      }
       else
       {
-        const u32 a1 = a0 + (nlo >= 2 ? 1u : 0u);
-        nx.start[a1] = p0 + (nlo >= 2 ? nlo : 0u);
+        const u32 a1 = a0 + (lo_act ? 1u : 0u);
+        nx.start[a1] = p0 + (lo_act ? nlo : 0u);
         nx.count[a1] = nhi;
         nx.rid[a1] = rid * 2 + 2;
         nx.row[a1] = (u32)hi_row;
@@ -142,7 +166,9 @@ k_scatter(SegLevel sg, const u32* __restrict__ seg_of, const u32* __restrict__ p
           u32 A, const u32* __restrict__ fbits, const u32* __restrict__ wpre, const u32* __restrict__ seg_nlo,
           const u32* __restrict__ seg_hbase, const u32* __restrict__ c_rows, const u64* __restrict__ c_actpos,
           u32 row_base_next, u32* __restrict__ perm_n, i64* __restrict__ pid_n, u32* __restrict__ seg_of_n,
-          i64* __restrict__ t_id, int* __restrict__ t_src, const u32* __restrict__ counters)
+          i64* __restrict__ t_id, int* __restrict__ t_src, const u32* __restrict__ counters,
+          const u64* __restrict__ c_sub, u32 t_sub, u32 sub_pos_base, u32* __restrict__ sub_perm,
+          i64* __restrict__ sub_pid)
 {
   const u32 p = blockIdx.x * 256u + threadIdx.x;
   if (p >= A || counters[1]) return;
@@ -153,11 +179,20 @@ k_scatter(SegLevel sg, const u32* __restrict__ seg_of, const u32* __restrict__ p
   const u32 hb = wpre[p >> 5] + __popc(w & ((1u << (p & 31)) - 1u)) - seg_hbase[s];
   const u32 r0 = row_base_next + c_rows[s];
   const u32 a0 = (u32)(c_actpos[s] >> 32), p0 = (u32)c_actpos[s];
+  const u32 q0 = sub_pos_base + (u32)c_sub[s];
+  const bool lo_sub = nlo >= 2 && nlo <= t_sub, hi_sub = nhi >= 2 && nhi <= t_sub;
+  const bool lo_act = nlo > 1 && !lo_sub;
   const u32 r = perm[p];
   const i64 id = pid[p];
   if (!hi)
   {
-    if (nlo >= 2)
+    if (lo_sub)
+    {
+      const u32 dst = q0 + (p - S) - hb;
+      sub_perm[dst] = r;
+      sub_pid[dst] = id;
+    }
+    else if (nlo >= 2)
     {
       const u32 dst = p0 + (p - S) - hb;
       perm_n[dst] = r;
@@ -172,12 +207,18 @@ k_scatter(SegLevel sg, const u32* __restrict__ seg_of, const u32* __restrict__ p
   }
   else
   {
-    if (nhi >= 2)
+    if (hi_sub)
     {
-      const u32 dst = p0 + (nlo >= 2 ? nlo : 0u) + hb;
+      const u32 dst = q0 + (lo_sub ? nlo : 0u) + hb;
+      sub_perm[dst] = r;
+      sub_pid[dst] = id;
+    }
+    else if (nhi >= 2)
+    {
+      const u32 dst = p0 + (lo_act ? nlo : 0u) + hb;
       perm_n[dst] = r;
       pid_n[dst] = id;
-      seg_of_n[dst] = a0 + (nlo >= 2 ? 1u : 0u);
+      seg_of_n[dst] = a0 + (lo_act ? 1u : 0u);
     }
     else
     {
@@ -196,9 +237,11 @@ __global__ void k_big_chunks(const u32* __restrict__ count, const u32* __restric
   chunks[i] = i < nbig ? (count[big_list[i]] + VI_CHUNK - 1) / VI_CHUNK : 0u;
 }
 
-__global__ void k_totals(const u32* c_rows, const u64* c_actpos, u32 R, const u32* counters, const u32* chunk_first,
-                         u32 chunk_bound, LevelTotals* out)
+__global__ void k_totals(const u32* c_rows, const u64* c_actpos, const u64* c_sub, u32 R, const u32* counters,
+                         const u32* chunk_first, u32 chunk_bound, LevelTotals* out)
 {
+  out->subs = (u32)(c_sub[R] >> 32);
+  out->subpos = (u32)c_sub[R];
   out->rows = c_rows[R];
   out->segs = (u32)(c_actpos[R] >> 32);
   out->pos = (u32)c_actpos[R];

@@ -38,13 +38,14 @@ _f32p = ctypes.POINTER(ctypes.c_float)
 class BuildInfo(ctypes.Structure):
     _fields_ = [("ranges", ctypes.c_int64), ("levels", ctypes.c_int32), ("mode", ctypes.c_int32),
                 ("point_visits", ctypes.c_int64), ("kernel_launches", ctypes.c_int64), ("build_ms", ctypes.c_double),
-                ("q_exponent", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("q_exponent", ctypes.c_int32), ("reserved", ctypes.c_int32), ("subtree_ms", ctypes.c_double),
+                ("subtree_ranges", ctypes.c_int64)]
 
 
 class LevelInfo(ctypes.Structure):
     _fields_ = [("level", ctypes.c_int32), ("reserved", ctypes.c_int32), ("ranges", ctypes.c_int64),
                 ("points", ctypes.c_int64), ("rows_emitted", ctypes.c_int64), ("stats_ms", ctypes.c_double),
-                ("partition_ms", ctypes.c_double)]
+                ("partition_ms", ctypes.c_double), ("in_subtrees", ctypes.c_int64)]
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
@@ -209,7 +210,7 @@ class Context:
         return int(self._L.vi_range_count(self._h))
 
     def ranges(self):
-        """(rangeId, Dimension, Mid, Id) columns in breadth-first order."""
+        """(rangeId, Dimension, Mid, Id) columns, one row per range (unspecified order)."""
         k = self.range_count
         rid = np.empty(k, np.int64)
         dim = np.empty(k, np.int32)
@@ -430,8 +431,8 @@ class IndexBuilder:
 
         `points`: iterable of (id, vector) -- enumerated once -- or a tuple (ids[n], rows[n, d]).
         `storeFactory(rangeId, capacity)` is accepted for signature compatibility; child ranges never leave the
-        device, so it is not called.  Rows come in breadth-first order (the reference yields depth-first; consumers
-        key by rangeId, Program.cs:18-26)."""
+        device, so it is not called.  Row order differs from the reference's depth-first order; consumers key by
+        rangeId (Program.cs:18-26)."""
         ctx = context or Context(device)
         try:
             first = True
