@@ -143,16 +143,47 @@ def gen_queries(rows_d, nq, seed):
     return torch.cat([a, b], 0).contiguous()
 
 
-def cpu_baseline(rows_h, ids_h, sample_rows, threads=1):
-    """The literal oracle (port of IndexBuilder.cs) timed on the host: bounded sample of the same workload."""
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def pick_threads(ids, rows):
+    """Thread count that actually runs the CPU arm fastest on this host (a container may advertise cores it cannot
+    use: then more threads only add contention and the sequential run is the fair baseline)."""
+    import oracle
+    m = min(200_000, rows.shape[0])
+    best_t, best = 1, None
+    for t in sorted({1, host_threads()}):
+        t0 = time.perf_counter()
+        oracle.build_mt(ids[:m], rows[:m], t)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best_t, best = t, dt
+    return best_t
+
+
+def cpu_baseline(rows_h, ids_h, sample_rows):
+    """The reference algorithm on the host (oracle port, bit-identical tables): bounded sample of the same workload,
+    with every host thread (vi_oracle_mt.c: dimensions of big ranges and whole sub-trees in parallel) and, for
+    context, with one thread as the strictly sequential reference runs."""
     import oracle
     m = min(sample_rows, rows_h.shape[0])
+    threads = pick_threads(ids_h, rows_h)
     t0 = time.perf_counter()
-    tbl = oracle.build(ids_h[:m], rows_h[:m], oracle.MODE_LITERAL)
+    tbl = oracle.build_mt(ids_h[:m], rows_h[:m], threads)
     dt = time.perf_counter() - t0
+    m1 = min(m, 1_000_000)
+    t0 = time.perf_counter()
+    oracle.build(ids_h[:m1], rows_h[:m1], oracle.MODE_LITERAL)
+    dt1 = time.perf_counter() - t0
     return {"value": m / dt, "unit": "vectors/s", "cores": threads, "kind": "port",
-            "sample": f"first {m} rows of the workload, one full literal build (oracle/vi_oracle.c, "
-                      f"-O2 -ffp-contract=off), {dt:.2f} s, {len(tbl)} ranges",
+            "sample": f"first {m} rows of the workload, one full literal build with {threads} threads "
+                      f"(oracle/vi_oracle_mt.c, -O2 -ffp-contract=off), {dt:.2f} s, {len(tbl)} ranges",
+            "single_thread": {"value": m1 / dt1, "rows": m1, "seconds": dt1,
+                              "note": "oracle/vi_oracle.c, sequential like the reference"},
             "host_cores_available": os.cpu_count()}, tbl
 
 
@@ -165,10 +196,11 @@ def run_reference(args):
     import oracle
     n = args.ref_rows
     ids, rows = ds.unit_gaussian(n, DIMS, seed=SEED)
+    threads = pick_threads(ids, rows)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        tbl = oracle.build(ids, rows, oracle.MODE_LITERAL)
+        tbl = oracle.build_mt(ids, rows, threads)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
@@ -179,10 +211,11 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"deep-image-96-shaped synthetic {args.rows}x96 index build (IndexBuilder.Build)",
-                       "sample_rows": n, "mode": "literal float32 Welford (IndexBuilder.cs:175-197)"},
-            "cpu_baseline": {"value": v, "unit": "vectors/s", "cores": 1, "kind": "port",
+                       "sample_rows": n, "mode": "literal float32 Welford (IndexBuilder.cs:175-197)", "threads": threads},
+            "cpu_baseline": {"value": v, "unit": "vectors/s", "cores": threads, "kind": "port",
                              "sample": f"each step = one full literal build of a {n}-row sample of the workload "
-                                       f"(numpy seed {SEED}); the reference algorithm is strictly sequential",
+                                       f"(numpy seed {SEED}) with {threads} host threads (oracle/vi_oracle_mt.c; the "
+                                       f"reference itself is sequential, its arithmetic is kept bit for bit)",
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": v, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -342,6 +375,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dims", type=int, default=96, help="96 = BASELINE configs[1]; 768 with --rows 1000000 = configs[4]")
     ap.add_argument("--ref-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--queries", type=int, default=1_000_000)
@@ -350,6 +384,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    global DIMS
+    DIMS = args.dims
     claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
@@ -412,7 +448,11 @@ def main():
     n_stats_launch = sum(1 for l in levels if l.points > 0)
     roofline = {"bound": "hbm", "kernel": "k_stats_big_fast + k_stats_small_fast (statistics pass, one per tree level)",
                 "achieved": stats_b / (stats_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": stats_b / (stats_ms / 1e3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                "frac": stats_b / (stats_ms / 1e3) / 1e9 / peak, "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one k_stats_big_fast launch over 10M x 96 rows from
+                # `ncu --set full` (profiles/r1_ncu_final.md): 3.9606 GB + 4.4 MB for 3.96 GB of algorithmic bytes
+                "traffic": 3.965e9 if (n == 10_000_000 and DIMS == 96) else None,
+                "traffic_note": "per top-level launch (A = 10M points); algorithmic bytes of that launch 3.96e9",
                 "algorithmic_bytes_per_launch": stats_b / max(n_stats_launch, 1),
                 "avg_launch_ms": stats_ms / max(n_stats_launch, 1),
                 "whole_build": {"algorithmic_bytes": whole_b, "achieved": whole_b / (ms_per_step / 1e3) / 1e9,
@@ -431,7 +471,8 @@ def main():
               "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i64 (exact sums of 26-bit fixed-point f32 rows)",
               "data": "synthetic",
-              "config": {"workload": f"configs[1]: deep-image-96-angular-shaped synthetic {n}x{DIMS} index build on 1 B200",
+              "config": {"workload": (f"configs[1]: deep-image-96-angular-shaped synthetic {n}x{DIMS} index build on 1 B200"
+                                      if DIMS == 96 else f"configs[4]-shaped: synthetic {n}x{DIMS} index build on 1 B200"),
                          "mode": "fast (qfx: order-independent integer statistics, 26-bit fixed point)", "rows": n, "dims": DIMS,
                          "l2": "inputs (3.84 GB of rows per level) are larger than the 126 MB L2; no flush needed",
                          "ranges": int(info.ranges), "levels": int(info.levels)},

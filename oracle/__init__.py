@@ -28,8 +28,8 @@ _f32p = ctypes.POINTER(ctypes.c_float)
 
 def build_lib(force: bool = False) -> str:
     """Compile oracle/vi_oracle.c -> oracle/libvi_oracle.so (gcc, flags in oracle/Makefile)."""
-    src = os.path.join(_HERE, "vi_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("vi_oracle.c", "vi_oracle_mt.c", "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libvi_oracle.so"])
     return _LIB_PATH
 
@@ -47,6 +47,9 @@ def lib() -> ctypes.CDLL:
                                 ctypes.c_int64, _i64p, _i32p, _f32p, _i64p, _i64p]
         L.vio_build_ex.restype = ctypes.c_int
         L.vio_build_ex.argtypes = L.vio_build.argtypes + [ctypes.c_int64, ctypes.c_int, ctypes.c_int32]
+        L.vio_build_mt.restype = ctypes.c_int
+        L.vio_build_mt.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, _i64p, _f32p, ctypes.c_int64, _i64p,
+                                   _i32p, _f32p, _i64p, _i64p, ctypes.c_int]
         L.vio_search_batch.restype = ctypes.c_int
         L.vio_search_batch.argtypes = [ctypes.c_int64, _i64p, _i32p, _f32p, _i64p, ctypes.c_int32,
                                        ctypes.c_int64, _f32p, ctypes.c_int64, ctypes.c_float, ctypes.c_int64,
@@ -109,6 +112,28 @@ def build(ids: np.ndarray, rows: np.ndarray, mode: int = MODE_LITERAL, root_rid:
     order = np.argsort(rid[:k], kind="stable")
     return RangeTable(rid[:k][order].copy(), dim[:k][order].copy(), mid[:k][order].copy(), oid[:k][order].copy(),
                       rid[:k].copy())
+
+
+def build_mt(ids: np.ndarray, rows: np.ndarray, threads: int) -> RangeTable:
+    """The literal build with `threads` host threads (vi_oracle_mt.c): same table as build(), used as the CPU baseline."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    n, d = rows.shape
+    cap = 2 * n + n // 8 + 1024
+    rid = np.empty(cap, np.int64)
+    dim = np.empty(cap, np.int32)
+    mid = np.empty(cap, np.float32)
+    oid = np.empty(cap, np.int64)
+    cnt = ctypes.c_int64(0)
+    rc = lib().vio_build_mt(n, d, d, _p(ids, _i64p), _p(rows, _f32p), cap, _p(rid, _i64p), _p(dim, _i32p), _p(mid, _f32p),
+                            _p(oid, _i64p), ctypes.byref(cnt), threads)
+    if rc == -2:
+        raise OverflowError("rangeId overflow (IndexBuilder.cs:99,104 checked arithmetic)")
+    if rc != 0:
+        raise OracleError(f"vio_build_mt rc={rc}")
+    k = cnt.value
+    order = np.argsort(rid[:k], kind="stable")
+    return RangeTable(rid[:k][order].copy(), dim[:k][order].copy(), mid[:k][order].copy(), oid[:k][order].copy(), None)
 
 
 def qfx_exponent(rows: np.ndarray) -> int:

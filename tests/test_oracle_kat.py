@@ -239,3 +239,14 @@ def test_fast_mode_divergence(gen):
     print(f"{gen}: rows lit {len(lit)} fast {len(qfx)} common {len(common)} same-dim {same_dim} identical {same_row}; "
           f"on the same point sets (127 ranges): |fast-exact| {fast_err:.2e} |literal-exact| {lit_err:.2e} "
           f"|fast-literal| {fast_lit:.2e} (max|x| {scale:.3f})")
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_multithreaded_baseline_equals_sequential_oracle(threads):
+    # vi_oracle_mt.c (bench.py's CPU arm) must produce the literal table bit for bit
+    ids, rows = datasets.unit_gaussian(60_000, 24, seed=12)
+    ids = ids * 5 + 1
+    a = _tbl(ids, rows)
+    b = oracle.build_mt(ids, rows, threads)
+    assert np.array_equal(a.range_id, b.range_id) and np.array_equal(a.dimension, b.dimension)
+    assert np.array_equal(a.mid.view(np.uint32), b.mid.view(np.uint32)) and np.array_equal(a.id, b.id)

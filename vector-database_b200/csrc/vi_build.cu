@@ -368,7 +368,7 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   const u32 t_big_fast = env_u32("VI_B200_T_BIG", 1024, VI_MIN_BIG, VI_MAX_ROWS_PER_LANE);
   const u32 t_big_exact = env_u32("VI_B200_T_BIG_EXACT", 512, VI_MIN_BIG, 1u << 30);
   env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
-  env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 4, 1, 4);
+  env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 4, 0, 4);  // 0 = cp.async ring
   // sub-tree kernel (fast mode): as many rows as fit 12 KB of shared memory per warp, at most 32 (one point per lane)
   u32 sub_rows = std::min<u32>(32u, (u32)(12288 / (ctx->ld * 4)));
   if (sub_rows < 4 || mode != VI_MODE_FAST || ctx->ld > 128) sub_rows = 0;  // wider rows stay on the level path
@@ -417,17 +417,23 @@ static void launch_big_fast(vi_ctx* ctx, BuildEnv& env, const float* rows, int c
   SegLevel& sg = ctx->seg[cur];
   StatsOut sout{ctx->t_dim, ctx->t_mid, ctx->t_id};
   const int ld = ctx->ld, dims = ctx->dims;
+#define CALL_BIG_ARGS                                                                                              \
+  sg, ctx->big_list[cur], ctx->chunk_first, nbig, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, \
+      sout, ctx->gacc, allow_whole
 #define CALL_BIG(TS, CH, FULL)                                                                                     \
-  if (env.big_unroll >= 4)                                                                                         \
-    k_stats_big_fast<TS, CH, FULL, 4><<<chunks, 256, 0, st>>>(sg, ctx->big_list[cur], ctx->chunk_first, nbig,       \
-                                                              ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, \
-                                                              env.qinv, mx, sout, ctx->gacc, allow_whole);         \
+  if (env.big_unroll == 0)                                                                                         \
+  {                                                                                                                \
+    const size_t ring = (size_t)BIG_NST * CH * 256 * sizeof(float4);                                               \
+    cudaFuncSetAttribute(k_stats_big_fast<TS, CH, FULL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring); \
+    k_stats_big_fast<TS, CH, FULL, 0><<<chunks, 256, ring, st>>>(CALL_BIG_ARGS);                                   \
+  }                                                                                                                \
+  else if (env.big_unroll >= 4)                                                                                    \
+    k_stats_big_fast<TS, CH, FULL, 4><<<chunks, 256, 0, st>>>(CALL_BIG_ARGS);                                      \
   else                                                                                                             \
-    k_stats_big_fast<TS, CH, FULL, 2><<<chunks, 256, 0, st>>>(sg, ctx->big_list[cur], ctx->chunk_first, nbig,       \
-                                                              ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, \
-                                                              env.qinv, mx, sout, ctx->gacc, allow_whole)
+    k_stats_big_fast<TS, CH, FULL, 2><<<chunks, 256, 0, st>>>(CALL_BIG_ARGS)
   FAST_DISPATCH(env.shp, CALL_BIG);
 #undef CALL_BIG
+#undef CALL_BIG_ARGS
   ++env.launches;
 }
 

@@ -179,6 +179,15 @@ __device__ __forceinline__ float ldg_f_stream(const float* p)
   return r;
 }
 
+// one float of a row for the partition gather: ask L2 for the smallest fill it offers (a plain load of 4 bytes was
+// measured to move a whole 128-byte line from HBM: 1.36 GB per level at 10M points, profiles/r1_ncu_final.md)
+__device__ __forceinline__ float ldg_f_gather(const float* p)
+{
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
 // hi flags before position x: word prefix + bits below x in its word
 __device__ __forceinline__ u32 hi_before(const u32* __restrict__ wpre, const u32* __restrict__ fbits, u32 x)
 {

@@ -21,7 +21,7 @@ k_flags(SegLevel sg, const u32* __restrict__ seg_of, const u32* __restrict__ per
     const u32 s = seg_of[p];
     const int dim = sg.dim[s];
     const float mid = sg.mid[s];
-    const float v = rows[(size_t)perm[p] * ld + dim];
+    const float v = ldg_f_gather(rows + (size_t)perm[p] * ld + dim);
     hi = v > mid || (v == mid && pid[p] > sg.pivot[s]);
   }
   const u32 b = __ballot_sync(0xffffffffu, hi);

@@ -288,6 +288,9 @@ __device__ __forceinline__ void finalize_big_range(const SegLevel& sg, u32 s, u3
 // finished by its CTA straight from shared memory; otherwise the partial sums go to gacc with integer atomics
 // (order-independent, so the result does not depend on scheduling) and k_finalize_big_fast picks the split.
 // gacc per slot: [ld][S1, S2 limb0, S2 limb1] followed by the two id-sum words.
+constexpr int BIG_NST = 4;  // cp.async ring depth of the pipelined chunk kernel (rows in flight per team)
+
+// UNR: register-prefetch unroll depth, or 0 for the cp.async ring (dynamic shared memory BIG_NST*CH*256*16 bytes)
 template <int TS, int CH, bool FULL, int UNR>
 __global__ void __launch_bounds__(256, (TS * CH <= 32) ? 3 : 1)
 k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __restrict__ chunk_first, u32 nbig,
@@ -352,20 +355,65 @@ k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __res
     u64 s2[CH * 4];
 #pragma unroll
     for (int i = 0; i < CH * 4; ++i) { s1[i] = 0; s2[i] = 0; }
-#pragma unroll UNR
-    for (u32 j = team; j < m; j += NT)
+    if constexpr (UNR == 0)
     {
-      const u32 r = sperm[j];
-      const float4* rp = reinterpret_cast<const float4*>(rows + (size_t)r * ld);
-      float4 x[CH];
-#pragma unroll
-      for (int k = 0; k < CH; ++k)
+      // Rows staged through shared memory with cp.async: a thread copies exactly the CH x 16 bytes it consumes
+      // itself (thread-private ring slots: no barrier), so BIG_NST rows per team stay in flight without holding
+      // registers -- the register-prefetch variants below are latency-bound at 80 registers (profiles/).
+      extern __shared__ float4 s_ring[];  // [BIG_NST][CH][256]
+      auto issue = [&](u32 jj, int st)
       {
-        const int c = c0 + k * TS + tl;
-        x[k] = (FULL || c < C4) ? ldg_f4_stream(rp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        if (jj < m)
+        {
+          const float4* rp = reinterpret_cast<const float4*>(rows + (size_t)sperm[jj] * ld);
 #pragma unroll
-      for (int k = 0; k < CH; ++k) qfx_acc4(s1 + k * 4, s2 + k * 4, x[k], qk);
+          for (int k = 0; k < CH; ++k)
+          {
+            const int c = c0 + k * TS + tl;
+            if (FULL || c < C4)
+            {
+              const u32 dst = (u32)__cvta_generic_to_shared(&s_ring[(st * CH + k) * 256 + threadIdx.x]);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rp + c) : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+#pragma unroll
+      for (int st = 0; st < BIG_NST - 1; ++st) issue(team + st * NT, st);
+      int st = 0;
+      for (u32 j = team; j < m; j += NT)
+      {
+        issue(j + (BIG_NST - 1) * NT, (st + BIG_NST - 1) % BIG_NST);
+        asm volatile("cp.async.wait_group %0;" ::"n"(BIG_NST - 1) : "memory");
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+        {
+          const int c = c0 + k * TS + tl;
+          const float4 x = (FULL || c < C4) ? s_ring[(st * CH + k) * 256 + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+          qfx_acc4(s1 + k * 4, s2 + k * 4, x, qk);
+        }
+        st = (st + 1) % BIG_NST;
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    else
+    {
+#pragma unroll UNR
+      for (u32 j = team; j < m; j += NT)
+      {
+        const u32 r = sperm[j];
+        const float4* rp = reinterpret_cast<const float4*>(rows + (size_t)r * ld);
+        float4 x[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+        {
+          const int c = c0 + k * TS + tl;
+          x[k] = (FULL || c < C4) ? ldg_f4_stream(rp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k) qfx_acc4(s1 + k * 4, s2 + k * 4, x[k], qk);
+      }
     }
 #pragma unroll
     for (int k = 0; k < CH; ++k)
