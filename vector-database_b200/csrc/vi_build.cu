@@ -243,12 +243,22 @@ static int grow_table(vi_ctx* ctx, int64_t rows_needed, int64_t keep)
 // =============================================================================================================
 // kernel dispatch on the row width
 // =============================================================================================================
+static u32 env_u32(const char* name, u32 dflt, u32 lo, u32 hi)
+{
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  long x = strtol(v, nullptr, 10);
+  if (x < (long)lo) x = lo;
+  if (x > (long)hi) x = hi;
+  return (u32)x;
+}
+
 struct FastShape
 {
   int ts, ch;
   bool full;
 };
-static FastShape fast_shape(int ld)
+static FastShape fast_shape(int ld, bool warp_rows)
 {
   const int c4 = ld / 4;
   FastShape s;
@@ -260,6 +270,8 @@ static FastShape fast_shape(int ld)
   else if (c4 <= 96) s = {32, 3, false};
   else if (c4 <= 128) s = {32, 4, false};
   else s = {32, 6, false};  // wider rows take several column passes
+  // experiment knob: rows up to 128 floats wide with one float4 per lane of a whole warp (lanes >= c4 idle)
+  if (c4 <= 32 && warp_rows) s = {32, 1, false};
   s.full = (c4 == s.ts * s.ch);
   return s;
 }
@@ -273,7 +285,8 @@ static FastShape fast_shape(int ld)
 #define FAST_DISPATCH(shp, CALL)                                                   \
   do                                                                               \
   {                                                                                \
-    if (shp.ts == 8 && shp.ch == 1) FAST_DISPATCH2(8, 1, shp.full, CALL);          \
+    if (shp.ts == 32 && shp.ch == 1) FAST_DISPATCH2(32, 1, shp.full, CALL);        \
+    else if (shp.ts == 8 && shp.ch == 1) FAST_DISPATCH2(8, 1, shp.full, CALL);     \
     else if (shp.ts == 8 && shp.ch == 2) FAST_DISPATCH2(8, 2, shp.full, CALL);     \
     else if (shp.ts == 8 && shp.ch == 3) FAST_DISPATCH2(8, 3, shp.full, CALL);     \
     else if (shp.ts == 8 && shp.ch == 4) FAST_DISPATCH2(8, 4, shp.full, CALL);     \
@@ -290,16 +303,6 @@ static int exact_chx(int dims)
   if (dims <= 96) return 3;
   if (dims <= 128) return 4;
   return 8;
-}
-
-static u32 env_u32(const char* name, u32 dflt, u32 lo, u32 hi)
-{
-  const char* v = getenv(name);
-  if (!v || !*v) return dflt;
-  long x = strtol(v, nullptr, 10);
-  if (x < (long)lo) x = lo;
-  if (x > (long)hi) x = hi;
-  return (u32)x;
 }
 
 int vi_debug_divcheck_impl(vi_ctx* ctx, uint64_t seed, int64_t samples, int64_t* mismatches)
@@ -326,7 +329,8 @@ struct BuildEnv
   u32 t_team, t_big, big_unroll;
   u32 t_sub;  // ranges of 2..t_sub points are finished by the sub-tree kernel (0 = off)
   u32 sub_minb;
-  FastShape shp;
+  FastShape shp;      // team / warp-per-range kernels
+  FastShape shp_big;  // chunk kernel
   int chx;
   float qk;
   double qinv;
@@ -365,16 +369,21 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   // range-size classes (see vi_stats_fast.cuh / vi_stats_exact.cuh); defaults from scripts/sweep.py on 10M x 96
   // (profiles/r1_sweep.txt); the variables exist for such sweeps
   env.t_team = env_u32("VI_B200_T_TEAM", 32, 2, VI_MAX_ROWS_PER_LANE);
-  const u32 t_big_fast = env_u32("VI_B200_T_BIG", 1024, VI_MIN_BIG, VI_MAX_ROWS_PER_LANE);
+  const u32 t_big_fast = env_u32("VI_B200_T_BIG", 512, VI_MIN_BIG, VI_MAX_ROWS_PER_LANE);
   const u32 t_big_exact = env_u32("VI_B200_T_BIG_EXACT", 512, VI_MIN_BIG, 1u << 30);
   env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
-  env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 4, 0, 4);  // 0 = cp.async ring
+  env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 8, 0, 8);  // 0 = cp.async ring
   // sub-tree kernel (fast mode): as many rows as fit 12 KB of shared memory per warp, at most 32 (one point per lane)
   u32 sub_rows = std::min<u32>(32u, (u32)(12288 / (ctx->ld * 4)));
   if (sub_rows < 4 || mode != VI_MODE_FAST || ctx->ld > 128) sub_rows = 0;  // wider rows stay on the level path
   env.t_sub = std::min(env_u32("VI_B200_T_SUB", sub_rows, 0, 32), sub_rows);
   env.sub_minb = env_u32("VI_B200_SUB_MINB", 2, 2, 3);
-  env.shp = fast_shape(ctx->ld);
+  // Rows up to 128 floats wide: the chunk kernel reads a row with ONE float4 per lane of a whole warp (lanes beyond
+  // the row idle): 16 accumulator registers per lane instead of 48, 63 registers, unroll 8 -> 0.72 ms per 10M x 96
+  // level instead of 0.90 (profiles/r1_sweep.txt).  The small-range kernels keep 8-lane teams (bit 1 switches them).
+  const u32 wr = env_u32("VI_B200_WARP_ROWS", 1, 0, 3);
+  env.shp = fast_shape(ctx->ld, (wr & 2) != 0);
+  env.shp_big = fast_shape(ctx->ld, (wr & 1) != 0);
   env.chx = exact_chx(ctx->dims);
   env.qk = 1.0f;
   env.qinv = 1.0;
@@ -427,11 +436,13 @@ static void launch_big_fast(vi_ctx* ctx, BuildEnv& env, const float* rows, int c
     cudaFuncSetAttribute(k_stats_big_fast<TS, CH, FULL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring); \
     k_stats_big_fast<TS, CH, FULL, 0><<<chunks, 256, ring, st>>>(CALL_BIG_ARGS);                                   \
   }                                                                                                                \
+  else if (env.big_unroll >= 8)                                                                                    \
+    k_stats_big_fast<TS, CH, FULL, 8><<<chunks, 256, 0, st>>>(CALL_BIG_ARGS);                                      \
   else if (env.big_unroll >= 4)                                                                                    \
     k_stats_big_fast<TS, CH, FULL, 4><<<chunks, 256, 0, st>>>(CALL_BIG_ARGS);                                      \
   else                                                                                                             \
     k_stats_big_fast<TS, CH, FULL, 2><<<chunks, 256, 0, st>>>(CALL_BIG_ARGS)
-  FAST_DISPATCH(env.shp, CALL_BIG);
+  FAST_DISPATCH(env.shp_big, CALL_BIG);
 #undef CALL_BIG
 #undef CALL_BIG_ARGS
   ++env.launches;
@@ -561,7 +572,7 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
         VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)s.nbig * env.gstride * sizeof(u64), st));
         launch_big_fast(ctx, env, rows, cur, s.nbig, s.chunks, mx, 1);
         // ranges that fit one chunk and one column pass were finished by their CTA
-        const int single_pass = (ld / 4) <= shp.ts * shp.ch;
+        const int single_pass = (ld / 4) <= env.shp_big.ts * env.shp_big.ch;
         if (!single_pass || s.maxseg > VI_CHUNK)
         {
           k_finalize_big_fast<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, ctx->gacc, ld,

@@ -110,7 +110,7 @@ __device__ __forceinline__ float qfx_mid(i64 s1, u32 n, double qinv)
 }
 
 template <int TS, int CH, bool FULL, bool WPS>
-__global__ void __launch_bounds__(256, (TS * CH <= 32) ? 3 : 1)
+__global__ void __launch_bounds__(256, (CH == 1) ? 4 : ((TS * CH <= 32) ? 3 : 1))
 k_stats_small_fast(SegLevel sg, u32 R, u32 nmin, u32 nmax, const u32* __restrict__ perm, const i64* __restrict__ pid,
                    const float* __restrict__ rows, int ld, int dims, float qk, double qinv, int mx, StatsOut out)
 {
@@ -156,7 +156,7 @@ k_stats_small_fast(SegLevel sg, u32 R, u32 nmin, u32 nmax, const u32* __restrict
     {
       const u32 nxt = (jb + GS + gl < n) ? pp[jb + GS + gl] : 0u;  // prefetch the next block of row indexes
       const u32 m = min((u32)GS, n - jb);
-#pragma unroll 2
+#pragma unroll (CH == 1 ? 8 : 2)
       for (u32 j0 = 0; j0 < m; j0 += TPS)
       {
         const u32 jj = j0 + trow;
@@ -292,7 +292,7 @@ constexpr int BIG_NST = 4;  // cp.async ring depth of the pipelined chunk kernel
 
 // UNR: register-prefetch unroll depth, or 0 for the cp.async ring (dynamic shared memory BIG_NST*CH*256*16 bytes)
 template <int TS, int CH, bool FULL, int UNR>
-__global__ void __launch_bounds__(256, (TS * CH <= 32) ? 3 : 1)
+__global__ void __launch_bounds__(256, (CH == 1) ? 4 : ((TS * CH <= 32) ? 3 : 1))
 k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __restrict__ chunk_first, u32 nbig,
                  const u32* __restrict__ perm, const i64* __restrict__ pid, const float* __restrict__ rows, int ld,
                  int dims, float qk, double qinv, int mx, StatsOut out, u64* __restrict__ gacc, int allow_whole)
