@@ -110,7 +110,11 @@ def build_qfx(ids, rows):
         s1 = [int(v) for v in sub.sum(axis=0)]
         s2 = [sum(int(v) * int(v) for v in sub[:, j]) for j in range(sub.shape[1])]
         keys = [n * b - a * a for a, b in zip(s1, s2)]
-        if max(keys) < (n * n) << 20:
+        chosen = 0
+        for i in range(1, len(keys)):
+            if (keys[i] > keys[chosen]) if mx else (keys[i] < keys[chosen]):
+                chosen = i
+        if keys[chosen] < (n * n) << 20:
             # poorly resolved range: literal float32 Welford statistics (IndexBuilder.cs:159-197)
             mean = rows[pts[0]].copy()
             q = np.zeros_like(mean)

@@ -198,18 +198,17 @@ int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
       /* key K = n*S2 - S1^2 (exact, >= 0); even depth argmax, odd depth argmin, lowest index wins ties */
       u128 bestk = 0;
       u128 thr = ((u128)(uint64_t)count * (u128)(uint64_t)count) << (2 * VIO_QFX_MIN_RES_BITS);
-      int resolved = 0;
       for (int32_t i = 0; i < d; ++i)
       {
         i128 a = (i128)s1[i];
         u128 k = (u128)(uint64_t)count * s2[i] - (u128)(a * a);
-        if (k >= thr) resolved = 1;
         if (i == 0 || (it.max ? (k > bestk) : (k < bestk))) { bestk = k; index = i; }
       }
       mid = (float)(((double)s1[index] / (double)count) * qinv);
-      /* Poorly resolved range: no dimension spreads over 2^10 quantisation steps (stdev), so the integer
-       * statistics cannot separate its points; it takes the reference's own float32 statistics instead. */
-      if (!resolved) { literal = 1; idn = 0; index = 0; }
+      /* Poorly resolved range: the CHOSEN dimension spreads over fewer than 2^10 quantisation steps (stdev), so the
+       * integer statistics cannot place Mid between its points; the range takes the reference's own float32
+       * statistics instead (on max-variance levels this means no dimension is resolved). */
+      if (bestk < thr) { literal = 1; idn = 0; index = 0; }
     }
     if (literal)
     {

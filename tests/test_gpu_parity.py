@@ -266,3 +266,54 @@ def test_cpp_host_mirror_main_test(mode):
     want = {int(r): (int(d), int(np.float32(m).view(np.uint32)), int(i))
             for r, d, m, i in zip(ref.range_id, ref.dimension, ref.mid, ref.id)}
     assert got == want
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_nan_rows_overflow_like_the_reference(mode):
+    # NaN components never compare greater than Mid, such points go low forever and the reference
+    # dies with OverflowException at depth 62 (IndexBuilder.cs:99).  Oracle and CUDA path must agree on that.
+    ids, rows = ds.uniform(300, 5, seed=2)
+    rows = rows.copy()
+    rows[10] = np.nan
+    rows[11] = np.nan
+    with pytest.raises(OverflowError):
+        oracle.build(ids, rows, mode)
+    with vi.Context(0) as ctx:
+        ctx.reserve(300, 5)
+        ctx.add(ids, rows)
+        with pytest.raises(OverflowError):
+            ctx.build(mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_single_nan_point_is_isolated(mode):
+    # one NaN point ends up alone in a leaf: the build succeeds and matches the oracle
+    ids, rows = ds.uniform(200, 4, seed=6)
+    rows = rows.copy()
+    rows[7, 2] = np.nan
+    assert_same_table(ids, rows, mode)
+
+
+def test_rebuild_and_mode_switch_on_one_context():
+    # buffers are reused across builds and modes; results must not depend on what ran before
+    ids, rows = ds.unit_gaussian(20_000, 96, seed=31)
+    with vi.Context(0) as ctx:
+        ctx.reserve(len(ids), 96)
+        ctx.add(ids, rows)
+        got = {}
+        for mode in (vi.MODE_FAST, vi.MODE_EXACT, vi.MODE_FAST, vi.MODE_EXACT):
+            ctx.build(mode)
+            rid, dim, mid, oid = ctx.ranges()
+            o = np.argsort(rid)
+            cur = (rid[o], dim[o], mid[o].view(np.uint32), oid[o])
+            if mode in got:
+                assert all(np.array_equal(a, b) for a, b in zip(got[mode], cur))
+            got[mode] = cur
+        # smaller data set on the same context afterwards
+        ctx.reserve(100, 96)
+        ctx.add(ids[:100], rows[:100])
+        ctx.build(vi.MODE_EXACT)
+        rid, dim, mid, oid = ctx.ranges()
+    ref = oracle.build(ids[:100], rows[:100])
+    o = np.argsort(rid)
+    assert np.array_equal(rid[o], ref.range_id) and np.array_equal(mid[o].view(np.uint32), ref.mid.view(np.uint32))

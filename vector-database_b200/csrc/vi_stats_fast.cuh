@@ -4,7 +4,7 @@
 // QBITS = 26, and the per-(range, dim) sums S1 = sum xi and S2 = sum xi^2 are EXACT integers, so any reduction
 // order -- lanes, teams, CTAs, atomics, GPUs -- gives the same bits.  Split choice: K = n*S2 - S1^2 (exact,
 // 128 bits), arg-max on even depths and arg-min on odd depths, lowest index on ties;
-// Mid = float((double)S1 / n * 2^(E-QBITS)).  A range in which no dimension has K >= n^2 * 2^20 (stdev below 2^10
+// Mid = float((double)S1 / n * 2^(E-QBITS)).  A range whose CHOSEN dimension has K < n^2 * 2^20 (stdev below 2^10
 // quantisation steps) takes the reference's float32 statistics instead (welford_team).  The CPU statement of the
 // same rules is oracle/vi_oracle.c mode 1.
 //
@@ -137,7 +137,6 @@ k_stats_small_fast(SegLevel sg, u32 R, u32 nmin, u32 nmax, const u32* __restrict
   const u32* pp = perm + S;
   const i64 id0 = (gl < n) ? pid[S + gl] : 0;  // issued early: its latency hides behind the row loads
   const Key128 thr = qfx_threshold(n);
-  bool ok = false;
   QfxBest best;
   best.key.hi = 0;
   best.key.lo = 0;
@@ -199,7 +198,6 @@ k_stats_small_fast(SegLevel sg, u32 R, u32 nmin, u32 nmax, const u32* __restrict
         if (d < dims)
         {
           const Key128 key = qfx_key(n, s1[k * 4 + e], s2[k * 4 + e], 0ull);
-          ok |= !key_lt(key, thr);
           if (qfx_better(mx != 0, key, d, best.key, best.idx))
           {
             best.key = key;
@@ -212,7 +210,7 @@ k_stats_small_fast(SegLevel sg, u32 R, u32 nmin, u32 nmax, const u32* __restrict
   best = qfx_reduce<TS>(best, mx != 0, tmask);
   int dim = best.idx;
   float mid = qfx_mid(best.s1, n, qinv);
-  if (!__any_sync(tmask, ok))
+  if (key_lt(best.key, thr))  // the chosen dimension is poorly resolved (uniform over the team after the reduction)
   {
     const ExBest eb = welford_team<TS, CH>(rows, ld, dims, pp, n, tl, tmask, mx != 0);
     dim = eb.idx;
@@ -244,7 +242,6 @@ __device__ __forceinline__ void finalize_big_range(const SegLevel& sg, u32 s, u3
                                                    u32* __restrict__ no_fallback_err = nullptr)
 {
   const Key128 thr = qfx_threshold(n);
-  bool ok = false;
   QfxBest best;
   best.key.hi = 0;
   best.key.lo = 0;
@@ -258,7 +255,6 @@ __device__ __forceinline__ void finalize_big_range(const SegLevel& sg, u32 s, u3
     const u64 s2lo = l0 + (l1 << 32);
     const u64 s2hi = (l1 >> 32) + ((s2lo < l0) ? 1ull : 0ull);
     const Key128 key = qfx_key(n, s1, s2lo, s2hi);
-    ok |= !key_lt(key, thr);
     if (qfx_better(mx != 0, key, d, best.key, best.idx))
     {
       best.key = key;
@@ -269,7 +265,7 @@ __device__ __forceinline__ void finalize_big_range(const SegLevel& sg, u32 s, u3
   best = qfx_reduce<32>(best, mx != 0, 0xffffffffu);
   int dim = best.idx;
   float mid = qfx_mid(best.s1, n, qinv);
-  if (!__any_sync(0xffffffffu, ok))
+  if (key_lt(best.key, thr))  // the chosen dimension is poorly resolved
   {
     if (no_fallback_err)
     {

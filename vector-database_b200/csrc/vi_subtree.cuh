@@ -152,7 +152,6 @@ k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ sub_perm, const i64
           }
         }
         const u64 thr = ((u64)m * (u64)m) << (2 * VI_QFX_MIN_RES_BITS);
-        bool ok = false;
         SubBest best;
         best.key = 0;
         best.s1 = 0;
@@ -167,7 +166,6 @@ k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ sub_perm, const i64
             {
               const i64 a = s1[c * 4 + e];
               const u64 key = (u64)m * s2[c * 4 + e] - (u64)(a * a);  // m <= 32: below 2^63, exact
-              ok |= key >= thr;
               if (sub_better(mx, key, d, best.key, best.idx))
               {
                 best.key = key;
@@ -187,7 +185,7 @@ k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ sub_perm, const i64
         }
         int dim = best.idx;
         float mid = m > 0 ? qfx_mid(best.s1, m, qinv) : 0.f;
-        const bool unresolved = act && !__any_sync(tmask, ok);
+        const bool unresolved = act && best.key < thr;  // chosen dimension poorly resolved (team-uniform)
         if (unresolved)
         {
           // poorly resolved: the reference's float32 recurrence over the same points in the same order
