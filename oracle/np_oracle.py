@@ -114,7 +114,7 @@ def build_qfx(ids, rows):
         for i in range(1, len(keys)):
             if (keys[i] > keys[chosen]) if mx else (keys[i] < keys[chosen]):
                 chosen = i
-        if keys[chosen] < (n * n) << 20:
+        if keys[chosen] < (n * n) << 10:
             # poorly resolved range: literal float32 Welford statistics (IndexBuilder.cs:159-197)
             mean = rows[pts[0]].copy()
             q = np.zeros_like(mean)

@@ -44,8 +44,8 @@ typedef unsigned __int128 u128;
 #define VIO_ERR_NOMEM -3
 #define VIO_ERR_ARG -4
 
-/* qfx mode: a range is "resolved" when some dimension has n^2 * var >= n^2 * 2^(2*10) in quantised units */
-#define VIO_QFX_MIN_RES_BITS 10
+/* qfx mode: a range is "resolved" when some dimension has n^2 * var >= n^2 * 2^(2*5) in quantised units */
+#define VIO_QFX_MIN_RES_BITS 5
 #define VIO_QBITS 26 /* fixed-point fraction bits: xi = rint(x * 2^(VIO_QBITS - E)), |xi| <= 2^26 */
 
 /* float.CompareTo as used by Comparer<float>.Default inside Enumerable.MaxBy (IndexBuilder.cs:77-79):
@@ -205,7 +205,7 @@ int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
         if (i == 0 || (it.max ? (k > bestk) : (k < bestk))) { bestk = k; index = i; }
       }
       mid = (float)(((double)s1[index] / (double)count) * qinv);
-      /* Poorly resolved range: the CHOSEN dimension spreads over fewer than 2^10 quantisation steps (stdev), so the
+      /* Poorly resolved range: the CHOSEN dimension spreads over fewer than 2^5 quantisation steps (stdev), so the
        * integer statistics cannot place Mid between its points; the range takes the reference's own float32
        * statistics instead (on max-variance levels this means no dimension is resolved). */
       if (bestk < thr) { literal = 1; idn = 0; index = 0; }

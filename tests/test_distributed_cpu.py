@@ -105,7 +105,7 @@ def emulate_rank(rank, world, ids, rows, coll):
             IDN = sum(p[2] for p in parts)
             n = sg["g"]
             keys = [n * b - a * a for a, b in zip(S1, S2)]
-            assert max(keys) >= (n * n) << 20, "poorly resolved range in the shared phase"
+            assert max(keys) >= (n * n) << 10, "poorly resolved range in the shared phase"
             dim = 0
             for j in range(1, len(keys)):
                 if (keys[j] > keys[dim]) if mx else (keys[j] < keys[dim]):

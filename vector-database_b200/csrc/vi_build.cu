@@ -9,6 +9,7 @@
 // parent is partitioned and drop out of the position space (it is compacted every level).
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -507,6 +508,8 @@ static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* 
   VI_CUDA_TRY(cudaStreamSynchronize(st));
   VI_CUDA_TRY(cudaGetLastError());
   const u32 overflow = (u32)(h[128] & 0xffffffffu), err = (u32)(h[128] >> 32);
+  if (getenv("VI_B200_TRACE")) fprintf(stderr, "[vi_b200] sub-trees %u, float32 fallbacks %u, overflow rows %u\n", s.sub_cnt,
+                                       (u32)(h[129] & 0xffffffffu), overflow);
   if (err == 1) return ctx->fail(VI_ERR_CAPACITY, "range table capacity exceeded (degenerate input: too many one-child ranges)");
   if (err == 2)
     return ctx->fail(VI_ERR_OVERFLOW, "rangeId overflow: a range at depth 62 still holds more than one point "

@@ -4,8 +4,8 @@
 // QBITS = 26, and the per-(range, dim) sums S1 = sum xi and S2 = sum xi^2 are EXACT integers, so any reduction
 // order -- lanes, teams, CTAs, atomics, GPUs -- gives the same bits.  Split choice: K = n*S2 - S1^2 (exact,
 // 128 bits), arg-max on even depths and arg-min on odd depths, lowest index on ties;
-// Mid = float((double)S1 / n * 2^(E-QBITS)).  A range whose CHOSEN dimension has K < n^2 * 2^20 (stdev below 2^10
-// quantisation steps) takes the reference's float32 statistics instead (welford_team).  The CPU statement of the
+// Mid = float((double)S1 / n * 2^(E-QBITS)).  A range whose CHOSEN dimension has K < n^2 * 2^10 (stdev below 2^5
+// quantisation steps: Mid's rounding error would exceed ~1.5 % of the spread) takes the reference's float32 statistics instead (welford_team).  The CPU statement of the
 // same rules is oracle/vi_oracle.c mode 1.
 //
 // |xi| <= 2^26, xi^2 <= 2^52: a lane that accumulates fewer than 4096 rows keeps S1 and S2 in one 64-bit register
@@ -63,7 +63,7 @@ __device__ __forceinline__ Key128 qfx_key(u32 n, i64 s1, u64 s2lo, u64 s2hi)
 }
 
 // n^2 * 2^(2*VI_QFX_MIN_RES_BITS)
-constexpr int VI_QFX_MIN_RES_BITS = 10;
+constexpr int VI_QFX_MIN_RES_BITS = 5;  // chosen dimension must spread over >= 2^5 quantisation steps (stdev)
 __device__ __forceinline__ Key128 qfx_threshold(u32 n)
 {
   const u64 n2 = (u64)n * (u64)n;

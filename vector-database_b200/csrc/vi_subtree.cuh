@@ -15,6 +15,7 @@
 // taken from an overflow area behind all blocks (atomic counter), so the table stays dense.
 #pragma once
 #include "vi_partition.cuh"
+#include "vi_stats_exact.cuh"
 #include "vi_stats_fast.cuh"
 
 struct SubList  // device arrays, one entry per sub-tree root
@@ -25,6 +26,14 @@ struct SubList  // device arrays, one entry per sub-tree root
   u32* row;
   u32* depth;
 };
+
+// RN(1/c) for the counts a sub-tree can see (host constant folding is IEEE division): the float32 fallback divides
+// through div_by_count (vi_stats_exact.cuh) instead of __fdiv_rn
+__constant__ float c_rcp32[33] = {
+    0.f,        1.f,        1.f / 2.f,  1.f / 3.f,  1.f / 4.f,  1.f / 5.f,  1.f / 6.f,  1.f / 7.f,  1.f / 8.f,
+    1.f / 9.f,  1.f / 10.f, 1.f / 11.f, 1.f / 12.f, 1.f / 13.f, 1.f / 14.f, 1.f / 15.f, 1.f / 16.f, 1.f / 17.f,
+    1.f / 18.f, 1.f / 19.f, 1.f / 20.f, 1.f / 21.f, 1.f / 22.f, 1.f / 23.f, 1.f / 24.f, 1.f / 25.f, 1.f / 26.f,
+    1.f / 27.f, 1.f / 28.f, 1.f / 29.f, 1.f / 30.f, 1.f / 31.f, 1.f / 32.f};
 
 constexpr int SUB_WARPS = 8;
 constexpr int SUB_NODES = 16;  // nodes with >= 2 points on one level of a sub-tree of <= 32 points
@@ -188,6 +197,7 @@ k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ sub_perm, const i64
         const bool unresolved = act && best.key < thr;  // chosen dimension poorly resolved (team-uniform)
         if (unresolved)
         {
+          if (tl == 0) atomicAdd(&counters[2], 1u);  // fallback count (diagnostics)
           // poorly resolved: the reference's float32 recurrence over the same points in the same order
           ExBest eb;
           eb.key = 0.f;
@@ -196,7 +206,8 @@ k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ sub_perm, const i64
           for (int d = tl; d < dims; d += 8)
           {
             float mean = wrows[(size_t)s_lp[warp][s0] * ld + d], q = 0.f;
-            for (u32 i = 1; i < m; ++i) welford_step(mean, q, wrows[(size_t)s_lp[warp][s0 + i] * ld + d], (float)(i + 1u));
+            for (u32 i = 1; i < m; ++i)
+              welford_step_r(mean, q, wrows[(size_t)s_lp[warp][s0 + i] * ld + d], (float)(i + 1u), c_rcp32[i + 1u]);
             const float key = mx ? q : -q;
             if (ex_better(key, d, eb.key, eb.idx))
             {
