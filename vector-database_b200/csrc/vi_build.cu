@@ -610,8 +610,14 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
       if (s.nbig)
       {
         const u32 nblk = (u32)((dims + 31) / 32);
-        k_stats_big_exact<<<s.nbig * nblk, 32, 0, st>>>(sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, dims,
-                                                        ctx->gstats);
+        const bool vec = ld % 4 == 0 && ((uintptr_t)rows & 15) == 0 && env_u32("VI_B200_EX_VEC", 1, 0, 1) != 0;
+        const u32 ng = env_u32("VI_B200_EX_NG", EXNG_DEFAULT, 4, 12);
+#define CALL_BIGEX(VEC, NG)                                                                                   \
+  k_stats_big_exact<VEC, NG><<<s.nbig * nblk, 32, 0, st>>>(sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, \
+                                                           dims, ctx->gstats)
+        if (vec) { if (ng <= 4) CALL_BIGEX(true, 4); else if (ng <= 6) CALL_BIGEX(true, 6); else CALL_BIGEX(true, 10); }
+        else { if (ng <= 4) CALL_BIGEX(false, 4); else if (ng <= 6) CALL_BIGEX(false, 6); else CALL_BIGEX(false, 10); }
+#undef CALL_BIGEX
         k_finalize_big_exact<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, ctx->gstats,
                                                                         ctx->pid[cur], dims, mx, sout);
         env.launches += 2;
