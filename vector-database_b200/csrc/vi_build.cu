@@ -18,7 +18,7 @@
 #include "vi_partition.cuh"
 #include "vi_scan.cuh"
 #include "vi_sharded.cuh"
-#include "vi_stats_exact.cuh"
+#include "vi_stats_exact_px.cuh"
 #include "vi_stats_fast.cuh"
 #include "vi_subtree.cuh"
 
@@ -610,6 +610,27 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
       if (s.nbig)
       {
         const u32 nblk = (u32)((dims + 31) / 32);
+        const bool vec_ok = ld % 4 == 0 && ((uintptr_t)rows & 15) == 0;
+        // top levels (few chains in the whole GPU): the warp-specialised pipeline, vi_stats_exact_px.cuh
+        const u32 px_max = env_u32("VI_B200_EX_PX", 2 * VI_NUM_SMS, 0, 1u << 20);
+        if (vec_ok && s.nbig * nblk <= px_max)
+        {
+          // > 48 KB of dynamic shared memory: opt in (per device; a handful of launches per build)
+          const u32 px_na = env_u32("VI_B200_EX_NA", 4, 4, 8), px_fma = env_u32("VI_B200_EX_FMA", 1, 0, 1);
+#define CALL_PX(NA, FMA)                                                                                          \
+  do                                                                                                              \
+  {                                                                                                               \
+    VI_CUDA_TRY(cudaFuncSetAttribute(k_stats_big_exact_px<NA, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     (int)sizeof(PxShared<NA>)));                                                 \
+    k_stats_big_exact_px<NA, FMA><<<s.nbig * nblk, 128, sizeof(PxShared<NA>), st>>>(                              \
+        sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, dims, ctx->gstats);                               \
+  } while (0)
+          if (px_na <= 4) { if (px_fma) CALL_PX(4, true); else CALL_PX(4, false); }
+          else { if (px_fma) CALL_PX(8, true); else CALL_PX(8, false); }
+#undef CALL_PX
+        }
+        else
+        {
         const bool vec = ld % 4 == 0 && ((uintptr_t)rows & 15) == 0 && env_u32("VI_B200_EX_VEC", 1, 0, 1) != 0;
         const u32 ng = env_u32("VI_B200_EX_NG", EXNG_DEFAULT, 4, 12);
 #define CALL_BIGEX(VEC, NG)                                                                                   \
@@ -618,6 +639,7 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
         if (vec) { if (ng <= 4) CALL_BIGEX(true, 4); else if (ng <= 6) CALL_BIGEX(true, 6); else CALL_BIGEX(true, 10); }
         else { if (ng <= 4) CALL_BIGEX(false, 4); else if (ng <= 6) CALL_BIGEX(false, 6); else CALL_BIGEX(false, 10); }
 #undef CALL_BIGEX
+        }
         k_finalize_big_exact<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, ctx->gstats,
                                                                         ctx->pid[cur], dims, mx, sout);
         env.launches += 2;

@@ -138,9 +138,9 @@ constexpr int EXNG_DEFAULT = 6;  // groups in flight (192 rows ahead of the recu
 // 24-bit significand of c), q0 is then the correctly rounded quotient unless C is all ones -- groups holding such a
 // count, operands outside [2^-60, 2^60] (not 0) and failed checks (about 2^-23 of the steps) redo their 32 steps
 // with div_by_count from the saved state.
-struct CountRcp  // per row of a group: c = (float)(Count + 1), r_hi, r_lo
+struct CountRcp  // per row of a group: r_hi, r_lo, c = (float)(Count + 1)
 {
-  float c, r_hi, r_lo, pad;
+  float r_hi, r_lo, c, pad;
 };
 
 __device__ __forceinline__ CountRcp count_rcp(u32 count_plus_1)
