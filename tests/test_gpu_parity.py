@@ -317,3 +317,47 @@ def test_rebuild_and_mode_switch_on_one_context():
     ref = oracle.build(ids[:100], rows[:100])
     o = np.argsort(rid)
     assert np.array_equal(rid[o], ref.range_id) and np.array_equal(mid[o].view(np.uint32), ref.mid.view(np.uint32))
+
+
+# ---- exact mode, top-level pipeline (vi_stats_exact_px.cuh): restart, safe-mode and tail paths ----------------------
+def _exact_equals_oracle(ids, rows):
+    assert_same_table(ids, rows, vi.MODE_EXACT)
+
+
+@pytest.mark.parametrize("n", [513, 544, 545, 4096 + 17, 30_001])
+def test_exact_pipeline_group_tails(n):
+    # (n - 1) % 32 covers 0, 31, 1 and odd sizes: full groups go through the pipeline, the tail through the safe steps
+    ids, rows = ds.unit_gaussian(n, 64, seed=n)
+    _exact_equals_oracle(ids, rows)
+
+
+def test_exact_pipeline_single_nan_restarts_then_safe_mode():
+    # one NaN component poisons its chain from that point on: every later group fails the quotient check, the pipeline
+    # restarts 16 times and then the variance warp finishes the range alone (same float32 recurrence, bit for bit)
+    ids, rows = ds.unit_gaussian(20_000, 64, seed=77)
+    rows = rows.copy()
+    rows[1234, 5] = np.nan
+    _exact_equals_oracle(ids, rows)
+
+
+def test_exact_pipeline_tiny_zero_and_offset_operands():
+    ids, rows = ds.unit_gaussian(24_000, 96, seed=78)
+    rows = rows.copy()
+    rows[:, 3] = 0.0                                   # d == 0 on every step
+    rows[:, 4] = np.float32(1e-40)                     # denormal constant
+    rows[::7, 5] = np.float32(3e-39)                   # denormal / zero mix: tiny non-zero differences (guard)
+    rows[1::7, 5] = 0.0
+    rows[:, 6] += np.float32(4096.0)                   # mean >> spread: quotients with heavy cancellation
+    rows[::1000, 7] = np.float32(3e38)                 # huge values: d overflows to inf in places
+    rows[:, 8] *= np.float32(1e-30)
+    _exact_equals_oracle(ids, rows)
+
+
+def test_exact_pipeline_count_with_all_ones_significand():
+    # Count + 1 = 2^24 - 1 has an all-ones significand: the one float for which the speculative quotient's check is
+    # not a proof, so its group takes the safe path (vi_stats_exact.cuh).  Needs > 2^24 points: 4 narrow dimensions.
+    n = (1 << 24) + 100
+    rng = np.random.default_rng(5)
+    rows = rng.standard_normal((n, 4), dtype=np.float32)
+    ids = np.arange(n, dtype=np.int64)
+    _exact_equals_oracle(ids, rows)

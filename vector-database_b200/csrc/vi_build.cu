@@ -612,22 +612,31 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
         const u32 nblk = (u32)((dims + 31) / 32);
         const bool vec_ok = ld % 4 == 0 && ((uintptr_t)rows & 15) == 0;
         // top levels (few chains in the whole GPU): the warp-specialised pipeline, vi_stats_exact_px.cuh
-        const u32 px_max = env_u32("VI_B200_EX_PX", 2 * VI_NUM_SMS, 0, 1u << 20);
+        const u32 px_max = env_u32("VI_B200_EX_PX", VI_NUM_SMS, 0, 1u << 20);
         if (vec_ok && s.nbig * nblk <= px_max)
         {
           // > 48 KB of dynamic shared memory: opt in (per device; a handful of launches per build)
-          const u32 px_na = env_u32("VI_B200_EX_NA", 4, 4, 8), px_fma = env_u32("VI_B200_EX_FMA", 1, 0, 1);
-#define CALL_PX(NA, FMA)                                                                                          \
-  do                                                                                                              \
-  {                                                                                                               \
-    VI_CUDA_TRY(cudaFuncSetAttribute(k_stats_big_exact_px<NA, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                     (int)sizeof(PxShared<NA>)));                                                 \
-    k_stats_big_exact_px<NA, FMA><<<s.nbig * nblk, 128, sizeof(PxShared<NA>), st>>>(                              \
-        sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, dims, ctx->gstats);                               \
-  } while (0)
-          if (px_na <= 4) { if (px_fma) CALL_PX(4, true); else CALL_PX(4, false); }
-          else { if (px_fma) CALL_PX(8, true); else CALL_PX(8, false); }
-#undef CALL_PX
+          VI_CUDA_TRY(cudaFuncSetAttribute(k_stats_big_exact_px<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sizeof(PxShared<16>)));
+          auto px_trace = [&](const char* what) -> int
+          {
+            if (!getenv("VI_B200_TRACE")) return VI_OK;
+            unsigned long long h[8][4];
+            VI_CUDA_TRY(cudaStreamSynchronize(st));
+            VI_CUDA_TRY(cudaMemcpyFromSymbol(h, g_px_dbg, sizeof(h)));
+            static const char* role[8] = {"chain", "verify0", "verify1", "variance", "-", "loader0", "loader1", "-"};
+            for (int w = 0; w < 8; ++w)
+              if (h[w][2])
+                fprintf(stderr, "[vi_b200] px %s level %d %-8s waitA %5.1f%% waitB %5.1f%% other %5.1f%% of %.2f Mcycles\n", what,
+                        s.level, role[w], 100.0 * h[w][0] / h[w][2], 100.0 * h[w][1] / h[w][2], 100.0 * h[w][3] / h[w][2],
+                        h[w][2] * 1e-6);
+            unsigned long long z[8][4] = {};
+            VI_CUDA_TRY(cudaMemcpyToSymbol(g_px_dbg, z, sizeof(z)));
+            return VI_OK;
+          };
+          k_stats_big_exact_px<16><<<s.nbig * nblk, PX_THREADS, sizeof(PxShared<16>), st>>>(
+              sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, dims, ctx->gstats);
+          px_trace("full");
         }
         else
         {
@@ -640,9 +649,14 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
         else { if (ng <= 4) CALL_BIGEX(false, 4); else if (ng <= 6) CALL_BIGEX(false, 6); else CALL_BIGEX(false, 10); }
 #undef CALL_BIGEX
         }
+        {
+          const u32 per = std::min(128u, std::max(1u, 2048u / s.nbig));
+          VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)s.nbig * 16, st));
+          k_idsum_big<<<s.nbig * per, 256, 0, st>>>(sg, ctx->big_list[cur], per, ctx->pid[cur], ctx->gacc);
+        }
         k_finalize_big_exact<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, ctx->gstats,
-                                                                        ctx->pid[cur], dims, mx, sout);
-        env.launches += 2;
+                                                                        ctx->gacc, dims, mx, sout);
+        env.launches += 3;
       }
       if (s.minseg < t_big)
       {

@@ -307,15 +307,60 @@ k_stats_big_exact(SegLevel sg, const u32* __restrict__ big_list, u32 nblk, const
   if (act) gstats[(size_t)slot * dims + col] = make_float2(mean, q);
 }
 
+// Id sums of the big ranges (Stats.IdN, IndexBuilder.cs:170,194), `per` CTAs per range: integer sums are order-free,
+// so they need not ride on the serial chains (one warp summing 10^7 ids costs more than a tenth of the level).
+__global__ void __launch_bounds__(256)
+k_idsum_big(SegLevel sg, const u32* __restrict__ big_list, u32 per, const i64* __restrict__ pid, u64* __restrict__ idacc)
+{
+  const u32 slot = blockIdx.x / per, b = blockIdx.x % per;
+  const u32 s = big_list[slot];
+  const u32 S = sg.start[s], n = sg.count[s];
+  u64 slo = 0;
+  i64 shi = 0;
+  for (u32 j = b * 256u + threadIdx.x; j < n; j += per * 256u)
+  {
+    const i64 id = pid[S + j];
+    slo += (u32)id;
+    shi += (id >> 32);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    slo += __shfl_xor_sync(0xffffffffu, slo, o);
+    shi += __shfl_xor_sync(0xffffffffu, shi, o);
+  }
+  __shared__ u64 w_lo[8];
+  __shared__ i64 w_hi[8];
+  if ((threadIdx.x & 31) == 0)
+  {
+    w_lo[threadIdx.x >> 5] = slo;
+    w_hi[threadIdx.x >> 5] = shi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    for (int w = 1; w < 8; ++w)
+    {
+      slo += w_lo[w];
+      shi += w_hi[w];
+    }
+    if (slo | (u64)shi)
+    {
+      atomicAdd(&idacc[2 * slot], slo);
+      atomicAdd(&idacc[2 * slot + 1], (u64)shi);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_finalize_big_exact(SegLevel sg, const u32* __restrict__ big_list, u32 nbig, const float2* __restrict__ gstats,
-                     const i64* __restrict__ pid, int dims, int mx, StatsOut out)
+                     const u64* __restrict__ idacc, int dims, int mx, StatsOut out)
 {
   const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= nbig) return;
   const u32 s = big_list[warp];
-  const u32 S = sg.start[s], n = sg.count[s];
+  const u32 n = sg.count[s];
   ExBest best;
   best.key = 0.f;
   best.mean = 0.f;
@@ -332,8 +377,7 @@ k_finalize_big_exact(SegLevel sg, const u32* __restrict__ big_list, u32 nbig, co
     }
   }
   best = ex_reduce(best);
-  const i64 pivot = range_mean_id<32>(pid + S, n, lane, 0xffffffffu);
-  if (lane == 0) write_split(sg, out, s, best.idx, best.mean, pivot);
+  if (lane == 0) write_split(sg, out, s, best.idx, best.mean, mean_id(idacc[2 * warp], (i64)idacc[2 * warp + 1], n));
 }
 
 // debug: compares div_by_count with __fdiv_rn on pseudo-random operands; returns the mismatch count
