@@ -92,6 +92,13 @@ int vi_points_reserve(vi_ctx* ctx, int64_t capacity, int32_t dims);
 int vi_points_add(vi_ctx* ctx, const int64_t* ids, const float* rows, int64_t n, int32_t dims);
 /* Same, from DEVICE memory on the ctx's device (device-to-device copy). */
 int vi_points_add_device(vi_ctx* ctx, const int64_t* d_ids, const float* d_rows, int64_t n, int32_t dims);
+/* The FileRangeStore record (FileRangeStore.cs:127-165): n records [int64 id][dims x float32], little endian, no
+ * padding.  From a host buffer, or streamed from a file (n < 0: to the end of the file) through two pinned buffers:
+ * the read of one batch overlaps the H2D copy and the de-interleave kernel of the one before.  read_ms / total_ms
+ * (either may be NULL) report the time inside fread and the whole call. */
+int vi_points_add_records(vi_ctx* ctx, const void* records, int64_t n, int32_t dims);
+int vi_points_add_file(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, int32_t dims, double* read_ms,
+                       double* total_ms);
 int64_t vi_points_count(const vi_ctx* ctx);
 
 /* ---- build: IndexBuilder.Build (IndexBuilder.cs:23-157) ------------------------------------------------------ */
@@ -108,6 +115,13 @@ int64_t vi_range_count(const vi_ctx* ctx);
  * dimension == -1 marks a leaf (RangeValue.Dimension), id is the leaf's point id there and the tie-break pivot
  * elsewhere (RangeValue.Id). */
 int vi_ranges_copy(const vi_ctx* ctx, int64_t* range_id, int32_t* dimension, float* mid, int64_t* id, int64_t cap);
+/* The inverse of vi_ranges_copy: rows (RangeID, Dimension, Mid, Id) in any order -- the reference consumer's
+ * Dictionary<long, RangeValue> (Program.cs:18-26) or its CSV "RangeID,Dimension,Mid,ID" (Program.cs:80,145-149) --
+ * become the context's searchable table (children linked by 2r+1 / 2r+2, an absent child stays absent).  The
+ * context then answers vi_search / vi_search_device; vi_search_verify needs the vectors and is refused.
+ * VI_ERR_INVALID_ARG: duplicate or negative RangeID, no row for RangeID 0, Dimension outside [-1, dims). */
+int vi_ranges_load(vi_ctx* ctx, const int64_t* range_id, const int32_t* dimension, const float* mid, const int64_t* id,
+                   int64_t n, int32_t dims);
 /* dbo.TextIndex form (DDL.sql:209-227): child RangeIDs or -1 for null, TextID = id for leaves and -1 (null)
  * for internal rows (DDL.sql:195-197), Dimension -1 / Mid NaN stand for null. */
 int vi_textindex_copy(const vi_ctx* ctx, int64_t* range_id, int16_t* dimension, float* mid, int64_t* low_range_id,

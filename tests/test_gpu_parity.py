@@ -361,3 +361,85 @@ def test_exact_pipeline_count_with_all_ones_significand():
     rows = rng.standard_normal((n, 4), dtype=np.float32)
     ids = np.arange(n, dtype=np.int64)
     _exact_equals_oracle(ids, rows)
+
+
+# ---- formats on either side of the path: record ingest, range-table import ----------------
+def _same_rows(got, want):
+    rid, dim, mid, oid = got
+    o = np.argsort(rid, kind="stable")
+    assert np.array_equal(rid[o], want[0]) and np.array_equal(dim[o], want[1]) and np.array_equal(oid[o], want[3])
+    assert np.array_equal(mid[o].view(np.uint32), want[2].view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_record_ingest_equals_array_ingest(mode, tmp_path):
+    # the FileRangeStore record [int64 id][dims x float32] from a buffer and streamed from a file (several batches,
+    # an offset, a padded row width) gives the same table as vi_points_add
+    ids, rows = ds.unit_gaussian(70_000, 50, seed=41)
+    ids = ids * 5 - 1000
+    want = gpu_table(ids, rows, mode)
+    rec = vi.pack_records(ids, rows)
+    path = tmp_path / "points.bin"
+    with open(path, "wb") as f:
+        f.write(b"x" * 24)          # a header the caller skips
+        f.write(rec.tobytes())
+    with vi.Context(0) as ctx:
+        ctx.reserve(10, 50)
+        ctx.add_records(rec[: 1000 * (8 + 200)], 50)
+        ctx.add_records(rec[1000 * (8 + 200):], 50)
+        assert ctx.count == 70_000
+        ctx.build(mode)
+        _same_rows(ctx.ranges(), want)
+    with vi.Context(0) as ctx:
+        ctx.reserve(0, 50)
+        read_ms, total_ms = ctx.add_file(str(path), 50, offset_bytes=24)
+        assert ctx.count == 70_000 and total_ms > 0
+        ctx.build(mode)
+        _same_rows(ctx.ranges(), want)
+        with pytest.raises(ValueError):
+            ctx.add_file(str(path), 50, offset_bytes=24, n=70_001)   # shorter than asked
+        with pytest.raises(ValueError):
+            ctx.add_file(str(path), 49, offset_bytes=24)             # "Invalid length of vector."
+
+
+def test_range_table_csv_round_trip_and_search(tmp_path):
+    # build -> CSV "RangeID,Dimension,Mid,ID" (Program.cs:145-149) -> shuffled import into a fresh context -> the same
+    # dbo.Search results, array for array
+    ids, rows = ds.unit_gaussian(30_000, 32, seed=43)
+    q = np.concatenate([rows[:200], ds.unit_gaussian(200, 32, seed=44)[1]])
+    with vi.Context(0) as ctx:
+        ctx.reserve(len(ids), 32)
+        ctx.add(ids, rows)
+        ctx.build(vi.MODE_EXACT)
+        rid, dim, mid, oid = ctx.ranges()
+        want0 = ctx.search(q, 0.0)
+        want1 = ctx.search(q, 0.05)
+        ti = ctx.textindex()
+    path = str(tmp_path / "index.csv")
+    vi.write_csv(path, rid, dim, mid, oid)
+    r2, d2, m2, o2 = vi.read_csv(path)
+    assert np.array_equal(r2, rid) and np.array_equal(d2, dim) and np.array_equal(o2, oid)
+    assert np.array_equal(m2.view(np.uint32), mid.view(np.uint32))      # text round trip is exact
+    perm = np.random.default_rng(1).permutation(len(r2))
+    with vi.Context(0) as ctx:
+        ctx.load_ranges(r2[perm], d2[perm], m2[perm], o2[perm], 32)
+        assert ctx.range_count == len(rid)
+        for want, p in ((want0, 0.0), (want1, 0.05)):
+            offs, out = ctx.search(q, p)
+            assert np.array_equal(offs, want[0]) and np.array_equal(out, want[1])
+        # same dbo.TextIndex rows (keyed by RangeID)
+        t2 = ctx.textindex()
+        o1, o2_ = np.argsort(ti[0]), np.argsort(t2[0])
+        for a, b in zip(ti, t2):
+            assert np.array_equal(a[o1], b[o2_], equal_nan=True)
+        with pytest.raises(vi.VectorIndexError):
+            ctx.search_verify(q[:4], 0.05, 0.1)                           # no vectors behind an imported table
+        # malformed tables
+        with pytest.raises(ValueError):
+            ctx.load_ranges(np.array([0, 1, 1]), np.array([0, -1, -1]), np.zeros(3, np.float32), np.array([1, 2, 3]), 32)
+        with pytest.raises(ValueError):
+            ctx.load_ranges(np.array([1, 2]), np.array([-1, -1]), np.zeros(2, np.float32), np.array([1, 2]), 32)
+        with pytest.raises(ValueError):
+            ctx.load_ranges(np.array([0]), np.array([32]), np.zeros(1, np.float32), np.array([1]), 32)
+        ctx.load_ranges(np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, np.int64), 32)
+        assert ctx.range_count == 0

@@ -30,6 +30,9 @@ internal static partial class NativeMethods
   [LibraryImport(Lib)] public static partial int vi_build(IntPtr ctx, int mode, out BuildInfo info);
   [LibraryImport(Lib)] public static partial long vi_range_count(IntPtr ctx);
   [LibraryImport(Lib)] public static unsafe partial int vi_ranges_copy(IntPtr ctx, long* rangeId, int* dimension, float* mid, long* id, long cap);
+  [LibraryImport(Lib)] public static unsafe partial int vi_ranges_load(IntPtr ctx, long* rangeId, int* dimension, float* mid, long* id, long n, int dims);
+  [LibraryImport(Lib)] public static unsafe partial int vi_points_add_records(IntPtr ctx, void* records, long n, int dims);
+  [LibraryImport(Lib, StringMarshalling = StringMarshalling.Utf8)] public static partial int vi_points_add_file(IntPtr ctx, string path, long offsetBytes, long n, int dims, out double readMs, out double totalMs);
   [LibraryImport(Lib)] public static unsafe partial int vi_textindex_copy(IntPtr ctx, long* rangeId, short* dimension, float* mid, long* low, long* high, long* textId, long cap);
   [LibraryImport(Lib)] public static unsafe partial int vi_search(IntPtr ctx, float* queries, long nq, int dims, float proximity, long* offsets, long* ids, long cap, out long total);
   [LibraryImport(Lib)] public static unsafe partial int vi_search_verify(IntPtr ctx, float* queries, long nq, int dims, float proximity, float distance, long* offsets, long* ids, long cap, out long total);

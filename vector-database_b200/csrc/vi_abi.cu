@@ -22,6 +22,10 @@ static int grow(vi_ctx* ctx, T** buf, int64_t* cap, int64_t need)
   return VI_OK;
 }
 
+int vi_ranges_load_impl(vi_ctx* ctx, const int64_t* rid, const int32_t* dim, const float* mid, const int64_t* id, int64_t n);
+int vi_points_add_records_impl(vi_ctx* ctx, const void* records, int64_t n);
+int vi_points_add_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, double* read_ms, double* total_ms);
+
 extern "C" {
 
 int vi_abi_version(void) { return VI_ABI_VERSION; }
@@ -122,6 +126,22 @@ int vi_points_reserve(vi_ctx* ctx, int64_t capacity, int32_t dims)
   return reserve_points(ctx, capacity);
 }
 
+}  // extern "C"
+
+// room for n more points (vi_table.cu's record ingest)
+int vi_reserve_for_add(vi_ctx* ctx, int64_t n)
+{
+  if (ctx->n + n > ctx->capacity)
+  {
+    int64_t want = ctx->capacity * 2;
+    if (want < ctx->n + n) want = ctx->n + n;
+    return reserve_points(ctx, want);
+  }
+  return VI_OK;
+}
+
+extern "C" {
+
 static int add_points(vi_ctx* ctx, const int64_t* ids, const float* rows, int64_t n, int32_t dims, cudaMemcpyKind kind)
 {
   if (!ctx) return VI_ERR_INVALID_ARG;
@@ -161,6 +181,30 @@ int vi_points_add(vi_ctx* ctx, const int64_t* ids, const float* rows, int64_t n,
 int vi_points_add_device(vi_ctx* ctx, const int64_t* d_ids, const float* d_rows, int64_t n, int32_t dims)
 {
   return add_points(ctx, d_ids, d_rows, n, dims, cudaMemcpyDeviceToDevice);
+}
+
+int vi_points_add_records(vi_ctx* ctx, const void* records, int64_t n, int32_t dims)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (ctx->dims == 0) return ctx->fail(VI_ERR_STATE, "vi_points_reserve must be called first");
+  if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid length of vector.");  // FileRangeStore.cs:59-64
+  if (n < 0 || (n > 0 && !records)) return ctx->fail(VI_ERR_INVALID_ARG, "null records");
+  if (n == 0) return VI_OK;
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->built = false;
+  return vi_points_add_records_impl(ctx, records, n);
+}
+
+int vi_points_add_file(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, int32_t dims, double* read_ms,
+                       double* total_ms)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (ctx->dims == 0) return ctx->fail(VI_ERR_STATE, "vi_points_reserve must be called first");
+  if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid length of vector.");
+  if (!path || offset_bytes < 0) return ctx->fail(VI_ERR_INVALID_ARG, "bad record file arguments");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->built = false;
+  return vi_points_add_file_impl(ctx, path, offset_bytes, n, read_ms, total_ms);
 }
 
 int64_t vi_points_count(const vi_ctx* ctx) { return ctx ? ctx->n : 0; }
@@ -205,6 +249,24 @@ int vi_ranges_copy(const vi_ctx* cctx, int64_t* range_id, int32_t* dimension, fl
   if (id) VI_CUDA_TRY(cudaMemcpyAsync(id, ctx->t_id, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
   VI_CUDA_TRY(cudaStreamSynchronize(st));
   return VI_OK;
+}
+
+int vi_ranges_load(vi_ctx* ctx, const int64_t* range_id, const int32_t* dimension, const float* mid, const int64_t* id,
+                   int64_t n, int32_t dims)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (dims <= 0 || dims > 32767) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid capacity or dimensions.");
+  if (ctx->dims != 0 && ctx->dims != dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");
+  if (n < 0 || n >= (int64_t)0x7fffffff || (n > 0 && (!range_id || !dimension || !mid || !id)))
+    return ctx->fail(VI_ERR_INVALID_ARG, "bad range table");
+  if (ctx->world > 1) return ctx->fail(VI_ERR_STATE, "vi_ranges_load on a multi-rank context: load on every rank of a world of 1");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (ctx->dims == 0)
+  {
+    ctx->dims = dims;
+    ctx->ld = (dims + 3) & ~3;
+  }
+  return vi_ranges_load_impl(ctx, range_id, dimension, mid, id, n);
 }
 
 int vi_textindex_copy(const vi_ctx* cctx, int64_t* range_id, int16_t* dimension, float* mid, int64_t* low_range_id,
@@ -314,7 +376,7 @@ int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims
   int64_t cand = 0;
   int* keep_src = ctx->search_src;
   ctx->search_src = nullptr;
-  if (ctx->replicated) return ctx->fail(VI_ERR_STATE, "candidate verification needs the vectors: not on a replicated table");
+  if (ctx->replicated) return ctx->fail(VI_ERR_STATE, "candidate verification needs the vectors: not on a replicated or imported table");
   rc = vi_search_impl(ctx, ctx->q_buf, nq, proximity, ctx->off_buf, nullptr, 0, &cand, nullptr, false);
   ctx->search_src = keep_src;
   if (rc != VI_OK) return rc;

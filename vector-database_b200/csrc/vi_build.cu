@@ -208,6 +208,9 @@ static int alloc_table(vi_ctx* ctx, int64_t n)
   return VI_OK;
 }
 
+// a table of `rows` rows for vi_ranges_load (vi_table.cu)
+int vi_alloc_table_rows(vi_ctx* ctx, int64_t rows) { return alloc_table(ctx, rows / 2 + 1); }
+
 // grows the table to hold `rows_needed` rows, keeping the first `keep` rows (multi-rank build: the shared top rows
 // exist before a rank learns how many points it will own)
 template <typename T>

@@ -53,8 +53,8 @@ ALLTOALLV_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 
 # every symbol include/vi_b200.h declares
 EXPORTS = ["vi_abi_version", "vi_create", "vi_destroy", "vi_last_error", "vi_points_reserve", "vi_points_add",
-           "vi_points_add_device", "vi_points_count", "vi_build", "vi_build_levels", "vi_range_count",
-           "vi_ranges_copy", "vi_textindex_copy", "vi_search", "vi_search_device", "vi_search_verify",
+           "vi_points_add_device", "vi_points_add_records", "vi_points_add_file", "vi_points_count", "vi_build",
+           "vi_build_levels", "vi_range_count", "vi_ranges_copy", "vi_ranges_load", "vi_textindex_copy", "vi_search", "vi_search_device", "vi_search_verify",
            "vi_set_collective", "vi_shared_rows", "vi_table_replicate", "vi_table_device", "vi_stream", "vi_debug_divcheck"]
 
 _lib = None
@@ -87,6 +87,10 @@ def load_library() -> ctypes.CDLL:
     L.vi_range_count.restype = ctypes.c_int64
     L.vi_ranges_copy.argtypes = [vp, _i64p, _i32p, _f32p, _i64p, ctypes.c_int64]
     L.vi_textindex_copy.argtypes = [vp, _i64p, _i16p, _f32p, _i64p, _i64p, _i64p, ctypes.c_int64]
+    L.vi_ranges_load.argtypes = [vp, _i64p, _i32p, _f32p, _i64p, ctypes.c_int64, ctypes.c_int32]
+    L.vi_points_add_records.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32]
+    L.vi_points_add_file.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.vi_search.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, _i64p, _i64p, ctypes.c_int64,
                             _i64p]
     L.vi_search_device.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, vp, vp, ctypes.c_int64,
@@ -188,6 +192,21 @@ class Context:
     def add_device(self, d_ids_ptr: int, d_rows_ptr: int, n: int, dims: int):
         self._check(self._L.vi_points_add_device(self._h, d_ids_ptr, d_rows_ptr, n, dims))
 
+    def add_records(self, records, dims: int):
+        """n records [int64 id][dims x float32] (the FileRangeStore layout, FileRangeStore.cs:127-165) in one buffer."""
+        buf = np.ascontiguousarray(np.frombuffer(records, np.uint8) if not isinstance(records, np.ndarray) else records)
+        rec = 8 + 4 * dims
+        if buf.nbytes % rec:
+            raise ValueError("Invalid length of vector.")
+        self._check(self._L.vi_points_add_records(self._h, buf.ctypes.data, buf.nbytes // rec, dims))
+
+    def add_file(self, path: str, dims: int, offset_bytes: int = 0, n: int = -1):
+        """Streams records from a file (two pinned buffers). Returns (read_ms, total_ms)."""
+        rd, tot = ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self._L.vi_points_add_file(self._h, os.fsencode(path), offset_bytes, n, dims, ctypes.byref(rd),
+                                               ctypes.byref(tot)))
+        return rd.value, tot.value
+
     @property
     def count(self) -> int:
         return int(self._L.vi_points_count(self._h))
@@ -225,6 +244,18 @@ class Context:
         self._check(self._L.vi_ranges_copy(self._h, _p(rid, _i64p), _p(dim, _i32p), _p(mid, _f32p), _p(oid, _i64p),
                                            min(rid.shape[0], dim.shape[0], mid.shape[0], oid.shape[0])))
         return k
+
+    def load_ranges(self, rid: np.ndarray, dim: np.ndarray, mid: np.ndarray, oid: np.ndarray, dims: int):
+        """The inverse of ranges(): rows (RangeID, Dimension, Mid, Id) in any order become the searchable table."""
+        rid = np.ascontiguousarray(rid, np.int64)
+        dim = np.ascontiguousarray(dim, np.int32)
+        mid = np.ascontiguousarray(mid, np.float32)
+        oid = np.ascontiguousarray(oid, np.int64)
+        if not (rid.shape == dim.shape == mid.shape == oid.shape) or rid.ndim != 1:
+            raise ValueError("range table columns differ in length")
+        self._check(self._L.vi_ranges_load(self._h, _p(rid, _i64p), _p(dim, _i32p), _p(mid, _f32p), _p(oid, _i64p),
+                                           rid.shape[0], dims))
+        self.dims = dims
 
     def textindex(self):
         """dbo.TextIndex columns (DDL.sql:209-227): RangeID, Dimension, Mid, LowRangeID, HighRangeID, TextID."""
@@ -322,6 +353,60 @@ class Context:
 
 
 # ---- IRangeStore family (host-side staging; children of the split tree live on the device) -------------------------
+# ---- the formats on either side: CSV "RangeID,Dimension,Mid,ID" (Program.cs:80,145-149), FileRangeStore records ----
+CSV_HEADER = "RangeID,Dimension,Mid,ID"
+
+
+def _fmt_float32(x: np.float32) -> str:
+    # shortest string that round-trips the float32 (what float.ToString() gives on .NET Core 3.0+)
+    if np.isnan(x):
+        return "NaN"
+    if np.isinf(x):
+        return "Infinity" if x > 0 else "-Infinity"
+    return np.format_float_positional(x, unique=True, trim="-") if 1e-5 <= abs(float(x)) < 1e15 or x == 0 \
+        else np.format_float_scientific(x, unique=True, trim="-", exp_digits=2).replace("e", "E")
+
+
+def write_csv(path: str, rid, dim, mid, oid) -> None:
+    """One line per range, as Program.cs:145-149 writes them (any row order)."""
+    with open(path, "w", newline="") as f:
+        f.write(CSV_HEADER + "\r\n")
+        for r, d, m, i in zip(rid.tolist(), dim.tolist(), np.asarray(mid, np.float32), oid.tolist()):
+            f.write(f"{r},{d},{_fmt_float32(m)},{i}\r\n")
+
+
+def read_csv(path: str):
+    """-> (rid int64, dim int32, mid float32, id int64); Mid is parsed to the nearest float32 (round trip exact)."""
+    rid, dim, mid, oid = [], [], [], []
+    with open(path, "r", newline="") as f:
+        header = f.readline().strip()
+        if header != CSV_HEADER:
+            raise ValueError(f"not a range table CSV: header {header!r}")
+        for line in f:
+            line = line.strip()
+            if not line:
+                continue
+            a, b, c, d = line.split(",")
+            rid.append(int(a))
+            dim.append(int(b))
+            mid.append({"NaN": np.nan, "Infinity": np.inf, "-Infinity": -np.inf}.get(c, c))
+            oid.append(int(d))
+    # (each text is parsed straight to float32: going through float64 first could round twice)
+    return (np.array(rid, np.int64), np.array(dim, np.int32), np.array([np.float32(x) for x in mid], np.float32),
+            np.array(oid, np.int64))
+
+
+def pack_records(ids: np.ndarray, rows: np.ndarray) -> np.ndarray:
+    """[int64 id][dims x float32] records (FileRangeStore.cs:127-165) as one uint8 array."""
+    ids = np.ascontiguousarray(ids, np.int64)
+    rows = np.ascontiguousarray(rows, np.float32)
+    n, d = rows.shape
+    out = np.empty((n, 8 + 4 * d), np.uint8)
+    out[:, :8] = ids.view(np.uint8).reshape(n, 8)
+    out[:, 8:] = rows.view(np.uint8).reshape(n, 4 * d)
+    return out.reshape(-1)
+
+
 class IRangeStore:
     """VectorIndex/IRangeStore.cs:6-22."""
 
