@@ -95,7 +95,7 @@ int vi_points_add_device(vi_ctx* ctx, const int64_t* d_ids, const float* d_rows,
 /* The FileRangeStore record (FileRangeStore.cs:127-165): n records [int64 id][dims x float32], little endian, no
  * padding.  From a host buffer, or streamed from a file (n < 0: to the end of the file) through two pinned buffers:
  * the read of one batch overlaps the H2D copy and the de-interleave kernel of the one before.  read_ms / total_ms
- * (either may be NULL) report the time inside fread and the whole call. */
+ * (either may be NULL) report the time inside the file reads and the whole call. */
 int vi_points_add_records(vi_ctx* ctx, const void* records, int64_t n, int32_t dims);
 int vi_points_add_file(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, int32_t dims, double* read_ms,
                        double* total_ms);

@@ -11,8 +11,13 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cub/device/device_radix_sort.cuh>
+#include <thread>
+#include <vector>
 
 #include "vi_common.cuh"
 
@@ -228,6 +233,30 @@ int vi_points_add_records_impl(vi_ctx* ctx, const void* records, int64_t n)
   return VI_OK;
 }
 
+// reads [offset, offset + bytes) of fd into dst with a few threads (one thread copies out of the page cache at
+// ~8 GB/s, well below PCIe); false on a short read
+static bool parallel_pread(int fd, char* dst, size_t bytes, off_t offset, unsigned nthreads)
+{
+  std::atomic<bool> ok(true);
+  auto part = [&](size_t a, size_t b)
+  {
+    while (a < b)
+    {
+      const ssize_t g = pread(fd, dst + a, b - a, offset + (off_t)a);
+      if (g <= 0) { ok = false; return; }
+      a += (size_t)g;
+    }
+  };
+  nthreads = std::max(1u, std::min<unsigned>(nthreads, (unsigned)(bytes >> 20) + 1u));
+  std::vector<std::thread> th;
+  const size_t chunk = ((bytes + nthreads - 1) / nthreads + 4095) & ~(size_t)4095;
+  for (unsigned t = 1; t < nthreads; ++t)
+    if ((size_t)t * chunk < bytes) th.emplace_back(part, (size_t)t * chunk, std::min(bytes, (size_t)(t + 1) * chunk));
+  part(0, std::min(bytes, chunk));
+  for (auto& t : th) t.join();
+  return ok;
+}
+
 int vi_points_add_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, double* read_ms, double* total_ms)
 {
   const size_t rec_bytes = 8 + 4 * (size_t)ctx->dims;
@@ -239,14 +268,10 @@ int vi_points_add_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes,
     const int64_t size = (int64_t)ftello(f);
     n = size > offset_bytes ? (size - offset_bytes) / (int64_t)rec_bytes : 0;
   }
-  if (fseeko(f, (off_t)offset_bytes, SEEK_SET) != 0)
-  {
-    fclose(f);
-    return ctx->fail(VI_ERR_INVALID_ARG, "cannot seek in the record file");
-  }
   int rc = vi_reserve_for_add(ctx, n);
   if (rc != VI_OK) { fclose(f); return rc; }
-  const int64_t batch = std::max<int64_t>(1, (int64_t)((32u << 20) / rec_bytes));
+  const int64_t batch = std::max<int64_t>(1, (int64_t)((64u << 20) / rec_bytes));
+  const unsigned nread = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
   void* h[2] = {nullptr, nullptr};
   u32* d[2] = {nullptr, nullptr};
   cudaStream_t cs[2] = {nullptr, nullptr};
@@ -290,10 +315,11 @@ int vi_points_add_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes,
     if (e != cudaSuccess) break;
     timespec a, z;
     clock_gettime(CLOCK_MONOTONIC, &a);
-    const size_t got = fread(h[b], rec_bytes, (size_t)k, f);
+    const bool got = parallel_pread(fileno(f), (char*)h[b], (size_t)k * rec_bytes,
+                                    (off_t)offset_bytes + (off_t)((size_t)done * rec_bytes), nread);
     clock_gettime(CLOCK_MONOTONIC, &z);
     rd_ms += (z.tv_sec - a.tv_sec) * 1e3 + (z.tv_nsec - a.tv_nsec) * 1e-6;
-    if ((int64_t)got != k)
+    if (!got)
     {
       cleanup();
       ctx->n = n0;
