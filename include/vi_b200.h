@@ -144,6 +144,14 @@ int vi_search_device(vi_ctx* ctx, const float* d_queries, int64_t nq, int32_t di
  * sqrt, as MemoryVectorIndexTests.cs:209-217).  Same CSR two-call protocol as vi_search. */
 int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, float distance,
                      int64_t* offsets, int64_t* ids, int64_t cap, int64_t* total);
+/* Top-k over the candidates of the traversal (the quality layer README.md:102-103 aims at): every candidate's
+ * distance to its query -- float32 accumulation in index order like MemoryVectorIndexTests.cs:209-217 -- and the k
+ * nearest per query, ties in traversal order.  metric 0: Euclidean, 1: angular (1 - cosine).  ids / dist are
+ * [nq][k] (unused slots: -1 / +inf), count[q] = min(k, candidates of q); any of them may be NULL.
+ * Recall against exact k-NN is governed by proximity: the traversal returns the points whose every coordinate is
+ * within proximity of the query's, and more. */
+int vi_search_topk(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int32_t k, int32_t metric,
+                   int64_t* ids, float* dist, int32_t* count, int64_t* candidates);
 
 /* ---- multi-GPU (one process per GPU; the host supplies the collective, e.g. torch.distributed/NCCL) ----------- */
 /* A multi-rank vi_build (VI_MODE_FAST only: its integer sums are order-independent) treats the points added to the

@@ -58,6 +58,8 @@ def lib() -> ctypes.CDLL:
         L.vio_qfx_exponent.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64]
         L.vio_distance_l2.restype = ctypes.c_float
         L.vio_distance_l2.argtypes = [_f32p, _f32p, ctypes.c_int32]
+        L.vio_distance_angular.restype = ctypes.c_float
+        L.vio_distance_angular.argtypes = [_f32p, _f32p, ctypes.c_int32]
         _lib = L
     return _lib
 
@@ -169,3 +171,9 @@ def distance_l2(a: np.ndarray, b: np.ndarray) -> float:
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)
     return float(lib().vio_distance_l2(_p(a, _f32p), _p(b, _f32p), a.shape[0]))
+
+
+def distance_angular(a: np.ndarray, b: np.ndarray) -> float:
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    return float(lib().vio_distance_angular(_p(a, _f32p), _p(b, _f32p), a.shape[0]))

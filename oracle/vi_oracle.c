@@ -383,3 +383,16 @@ float vio_distance_l2(const float* a, const float* b, int32_t d)
   }
   return sqrtf(s);
 }
+
+/* angular distance 1 - a.b / (|a| |b|), float32 accumulation in index order (the top-k layer's second metric) */
+float vio_distance_angular(const float* a, const float* b, int32_t d)
+{
+  float dot = 0.0f, na = 0.0f, nb = 0.0f;
+  for (int32_t i = 0; i < d; ++i)
+  {
+    dot = dot + a[i] * b[i];
+    na = na + a[i] * a[i];
+    nb = nb + b[i] * b[i];
+  }
+  return 1.0f - dot / (sqrtf(na) * sqrtf(nb));
+}

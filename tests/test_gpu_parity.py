@@ -443,3 +443,58 @@ def test_range_table_csv_round_trip_and_search(tmp_path):
             ctx.load_ranges(np.array([0]), np.array([32]), np.zeros(1, np.float32), np.array([1]), 32)
         ctx.load_ranges(np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, np.int64), 32)
         assert ctx.range_count == 0
+
+
+# ---- top-k over the candidates ------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [0, 1])
+def test_topk_equals_oracle_candidates_sorted_by_distance(metric):
+    # oracle: dbo.Search candidates in traversal order, float32 distances accumulated in index order, stable sort
+    ids, rows = ds.unit_gaussian(20_000, 16, seed=51)
+    ids = ids * 3 + 1
+    row_of = {int(i): r for r, i in enumerate(ids)}
+    q = np.concatenate([rows[:30], ds.unit_gaussian(30, 16, seed=52)[1]])
+    table = oracle.build(ids, rows, vi.MODE_EXACT)
+    p, k = 0.25, 10
+    offs, cand, _ = oracle.search(table, q, p)
+    fn = oracle.distance_l2 if metric == 0 else oracle.distance_angular
+    with vi.Context(0) as ctx:
+        ctx.reserve(len(ids), 16)
+        ctx.add(ids, rows)
+        ctx.build(vi.MODE_EXACT)
+        got_ids, got_dist, got_cnt, ncand = ctx.search_topk(q, p, k, metric)
+        assert ncand == len(cand)
+        few_ids, few_dist, few_cnt, _ = ctx.search_topk(q, 0.0, 4, metric)   # p = 0: at most one candidate per query
+    assert (got_cnt > 3).any()
+    for i in range(len(q)):
+        c = cand[offs[i]:offs[i + 1]]
+        d = np.array([fn(rows[row_of[int(x)]], q[i]) for x in c], np.float32)
+        order = np.argsort(d, kind="stable")[:k]
+        n = len(order)
+        assert got_cnt[i] == n
+        assert np.array_equal(got_ids[i, :n], c[order])
+        assert np.array_equal(got_dist[i, :n].view(np.uint32), d[order].view(np.uint32))
+        assert np.all(got_ids[i, n:] == -1) and np.all(np.isinf(got_dist[i, n:]))
+    assert np.all(few_cnt[:30] == 1) and np.array_equal(few_ids[:30, 0], ids[:30]) and np.all(few_ids[:, 1:] == -1)
+
+
+def test_topk_recall_reaches_one_when_the_box_covers_the_neighbours():
+    # the traversal returns a superset of the L-infinity box of half-width p: with p >= the k-th neighbour's Euclidean
+    # distance the top-k over candidates IS the exact k-NN (brute force, float64)
+    ids, rows = ds.unit_gaussian(5000, 8, seed=53)
+    q = ds.unit_gaussian(40, 8, seed=54)[1]
+    k = 5
+    d2 = ((rows[None, :, :].astype(np.float64) - q[:, None, :].astype(np.float64)) ** 2).sum(axis=2)
+    exact = np.argsort(d2, axis=1, kind="stable")[:, :k]
+    p = float(np.sqrt(np.take_along_axis(d2, exact, axis=1)[:, -1].max())) * 1.0001
+    with vi.Context(0) as ctx:
+        ctx.reserve(len(ids), 8)
+        ctx.add(ids, rows)
+        ctx.build(vi.MODE_FAST)
+        got_ids, _, cnt, _ = ctx.search_topk(q, p, k, 0)
+        with pytest.raises(ValueError):
+            ctx.search_topk(q, p, 0, 0)
+        with pytest.raises(ValueError):
+            ctx.search_topk(q, p, 5, 7)
+    assert np.all(cnt == k)
+    for i in range(len(q)):
+        assert set(got_ids[i].tolist()) == set(ids[exact[i]].tolist())

@@ -35,6 +35,7 @@ internal static partial class NativeMethods
   [LibraryImport(Lib, StringMarshalling = StringMarshalling.Utf8)] public static partial int vi_points_add_file(IntPtr ctx, string path, long offsetBytes, long n, int dims, out double readMs, out double totalMs);
   [LibraryImport(Lib)] public static unsafe partial int vi_textindex_copy(IntPtr ctx, long* rangeId, short* dimension, float* mid, long* low, long* high, long* textId, long cap);
   [LibraryImport(Lib)] public static unsafe partial int vi_search(IntPtr ctx, float* queries, long nq, int dims, float proximity, long* offsets, long* ids, long cap, out long total);
+  [LibraryImport(Lib)] public static unsafe partial int vi_search_topk(IntPtr ctx, float* queries, long nq, int dims, float proximity, int k, int metric, long* ids, float* dist, int* count, out long candidates);
   [LibraryImport(Lib)] public static unsafe partial int vi_search_verify(IntPtr ctx, float* queries, long nq, int dims, float proximity, float distance, long* offsets, long* ids, long cap, out long total);
 
   /// <summary>Maps a status code back onto the exception the reference would have thrown.</summary>

@@ -25,6 +25,8 @@ static int grow(vi_ctx* ctx, T** buf, int64_t* cap, int64_t need)
 int vi_ranges_load_impl(vi_ctx* ctx, const int64_t* rid, const int32_t* dim, const float* mid, const int64_t* id, int64_t n);
 int vi_points_add_records_impl(vi_ctx* ctx, const void* records, int64_t n);
 int vi_points_add_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, double* read_ms, double* total_ms);
+int vi_search_topk_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proximity, int32_t k, int32_t metric,
+                        int64_t* ids, float* dist, int32_t* count, int64_t* candidates);
 
 extern "C" {
 
@@ -361,6 +363,21 @@ int vi_search(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float
   }
   ctx->search_src = keep_src;
   return rc;
+}
+
+int vi_search_topk(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int32_t k, int32_t metric,
+                   int64_t* ids, float* dist, int32_t* count, int64_t* candidates)
+{
+  if (!ctx) return VI_ERR_INVALID_ARG;
+  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");
+  if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !queries)) return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
+  if (k <= 0 || k > 1024 || (metric != 0 && metric != 1)) return ctx->fail(VI_ERR_INVALID_ARG, "k must be 1..1024, metric 0 or 1");
+  if (ctx->replicated) return ctx->fail(VI_ERR_STATE, "top-k needs the vectors: not on a replicated or imported table");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc = stage_queries(ctx, queries, nq);
+  if (rc != VI_OK) return rc;
+  return vi_search_topk_impl(ctx, ctx->q_buf, nq, proximity, k, metric, ids, dist, count, candidates);
 }
 
 int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, float distance,

@@ -54,7 +54,7 @@ ALLTOALLV_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 # every symbol include/vi_b200.h declares
 EXPORTS = ["vi_abi_version", "vi_create", "vi_destroy", "vi_last_error", "vi_points_reserve", "vi_points_add",
            "vi_points_add_device", "vi_points_add_records", "vi_points_add_file", "vi_points_count", "vi_build",
-           "vi_build_levels", "vi_range_count", "vi_ranges_copy", "vi_ranges_load", "vi_textindex_copy", "vi_search", "vi_search_device", "vi_search_verify",
+           "vi_build_levels", "vi_range_count", "vi_ranges_copy", "vi_ranges_load", "vi_textindex_copy", "vi_search", "vi_search_topk", "vi_search_device", "vi_search_verify",
            "vi_set_collective", "vi_shared_rows", "vi_table_replicate", "vi_table_device", "vi_stream", "vi_debug_divcheck"]
 
 _lib = None
@@ -97,6 +97,8 @@ def load_library() -> ctypes.CDLL:
                                    _i64p, _i64p]
     L.vi_search_verify.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_float, _i64p,
                                    _i64p, ctypes.c_int64, _i64p]
+    L.vi_search_topk.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_int32, ctypes.c_int32,
+                                 _i64p, _f32p, _i32p, _i64p]
     L.vi_set_collective.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ALLREDUCE_FN, ALLTOALLV_FN, vp]
     L.vi_shared_rows.argtypes = [vp, _i64p]
     L.vi_table_replicate.argtypes = [vp]
@@ -301,6 +303,18 @@ class Context:
                                              ctypes.c_float(distance), _p(offsets, _i64p), _p(ids, _i64p), total.value,
                                              ctypes.byref(total)))
         return offsets, ids[:total.value]
+
+    def search_topk(self, queries: np.ndarray, proximity: float, k: int, metric: int = 0):
+        """k nearest candidates per query: (ids[nq,k] (-1 = none), dist[nq,k] (+inf = none), count[nq], candidates)."""
+        queries = np.ascontiguousarray(queries, np.float32)
+        nq, d = queries.shape
+        ids = np.empty((nq, k), np.int64)
+        dist = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.int32)
+        cand = ctypes.c_int64(0)
+        self._check(self._L.vi_search_topk(self._h, _p(queries, _f32p), nq, d, proximity, k, metric, _p(ids, _i64p),
+                                           _p(dist, _f32p), _p(cnt, _i32p), ctypes.byref(cand)))
+        return ids, dist, cnt, cand.value
 
     def search_device(self, d_queries_ptr: int, nq: int, dims: int, proximity: float, d_offsets_ptr: int,
                       d_ids_ptr: int, cap: int):
