@@ -383,6 +383,8 @@ def main():
     ap.add_argument("--no-exact", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--topk", type=int, default=0, help="also measure recall@k / queries/s of vi_search_topk against "
+                    "exact k-NN (torch brute force as the checker) on 2000 fresh queries")
     ap.add_argument("--ingest-file", default="", help="also time vi_points_add_file: writes N records [int64 id]"
                     "[D x f32] (FileRangeStore layout) to this path, streams them back in, imports the built table")
     args = ap.parse_args()
@@ -565,6 +567,46 @@ def main():
                      "steps": len(e2e_ms), "warmup": 2,
                      "path": "vi_points_reserve + vi_points_add(host pinned) + vi_build(fast) + vi_ranges_copy(host pinned)"}
     log(f"e2e: {e2e:.1f} ms/step")
+    if args.topk > 0:
+        # quality layer: k nearest candidates vs exact k-NN
+        k, nq_t = args.topk, 2000
+        g = torch.Generator(device=dev)
+        g.manual_seed(99)
+        ctx.build(vi.MODE_FAST)
+        rows_dev = rows_h.to(dev)
+        # queries: dataset rows with N(0, 0.003^2) noise per coordinate, re-normalised (near-duplicate lookup).  On
+        # i.i.d. synthetic data the OTHER neighbours are far in most coordinates (nearest of 10M random unit vectors
+        # in 96-d is at distance ~1.2), so only the first neighbour can be inside a small box: recall@1 is the figure
+        # that says something here, recall@k is reported for completeness.
+        pick = torch.randint(0, n, (nq_t,), generator=g, device=dev)
+        qt = rows_dev[pick] + 0.003 * torch.randn((nq_t, DIMS), generator=g, device=dev, dtype=torch.float32)
+        qt = qt / qt.norm(dim=1, keepdim=True)
+        truth = torch.empty((nq_t, k), dtype=torch.int64, device=dev)
+        r2 = (rows_dev * rows_dev).sum(dim=1)
+        for s0 in range(0, nq_t, 250):     # exact k-NN, chunked (a 250 x 10M distance block is 10 GB)
+            qq = qt[s0:s0 + 250]
+            d2 = r2[None, :] - 2.0 * (qq @ rows_dev.T)
+            truth[s0:s0 + 250] = d2.topk(k, dim=1, largest=False).indices
+            del d2
+        truth_ids = ids_h.to(dev)[truth].cpu().numpy()
+        del rows_dev, r2
+        torch.cuda.empty_cache()
+        qn = qt.cpu().numpy()
+        topk = {}
+        for p in (0.01, 0.02, 0.03):
+            ctx.search_topk(qn[:64], p, k, 0)
+            t0 = time.perf_counter()
+            got, _, cnt, ncand = ctx.search_topk(qn, p, k, 0)
+            ms = (time.perf_counter() - t0) * 1e3
+            hit = sum(len(set(got[i, :cnt[i]].tolist()) & set(truth_ids[i].tolist())) for i in range(nq_t))
+            hit1 = sum(int(cnt[i] > 0 and got[i, 0] == truth_ids[i, 0]) for i in range(nq_t))
+            topk[f"p={p}"] = {"recall_at_1": hit1 / nq_t, "recall_at_k": hit / (nq_t * k),
+                              "queries_per_sec": nq_t / (ms / 1e3), "ms": ms, "candidates_per_query": ncand / nq_t}
+            log(f"top-{k} p={p}: recall@1 {hit1 / nq_t:.3f} recall@{k} {hit / (nq_t * k):.3f}, {ncand / nq_t:.0f} "
+                f"candidates/query, {ms:.1f} ms for {nq_t} queries")
+        result["topk"] = {"k": k, "queries": nq_t, "metric": "euclidean",
+                          "queries_are": "dataset rows + N(0, 0.003^2) noise per coordinate, re-normalised",
+                          "truth": "torch brute force (checker only)", **topk}
     if args.ingest_file:
         # formats on either side of the path: record-file ingest and range-table import
         rec = vi.pack_records(ids_np, rows_np)
