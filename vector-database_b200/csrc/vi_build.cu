@@ -97,8 +97,10 @@ void vi_free_workspace(vi_ctx* ctx)
     cudaFree(ctx->big_list[i]); ctx->big_list[i] = nullptr;
     SegLevel& s = ctx->seg[i];
     cudaFree(s.start); cudaFree(s.count); cudaFree(s.rid); cudaFree(s.row); cudaFree(s.dim); cudaFree(s.mid);
-    cudaFree(s.pivot);
+    cudaFree(s.pivot); cudaFree(s.bslot);
     s = SegLevel();
+    cudaFree(ctx->bl_parent[i]); ctx->bl_parent[i] = nullptr;
+    cudaFree(ctx->bl_sib[i]); ctx->bl_sib[i] = nullptr;
   }
   cudaFree(ctx->chunk_first); ctx->chunk_first = nullptr;
   cudaFree(ctx->fbits); ctx->fbits = nullptr;
@@ -118,6 +120,7 @@ void vi_free_workspace(vi_ctx* ctx)
   cudaFree(ctx->sub_depth); ctx->sub_depth = nullptr;
   cudaFree(ctx->sub_stats); ctx->sub_stats = nullptr;
   cudaFree(ctx->gacc); ctx->gacc = nullptr;
+  cudaFree(ctx->gacc_prev); ctx->gacc_prev = nullptr;
   cudaFree(ctx->gstats); ctx->gstats = nullptr;
   cudaFree(ctx->d_absmax); ctx->d_absmax = nullptr;
   if (ctx->totals) cudaFreeHost(ctx->totals);
@@ -163,6 +166,9 @@ static int alloc_workspace(vi_ctx* ctx, int64_t n)
     VI_CUDA_TRY(dalloc(&s.dim, maxseg));
     VI_CUDA_TRY(dalloc(&s.mid, maxseg));
     VI_CUDA_TRY(dalloc(&s.pivot, maxseg));
+    VI_CUDA_TRY(dalloc(&s.bslot, maxseg));
+    VI_CUDA_TRY(dalloc(&ctx->bl_parent[i], maxbig));
+    VI_CUDA_TRY(dalloc(&ctx->bl_sib[i], maxbig));
   }
   VI_CUDA_TRY(dalloc(&ctx->chunk_first, maxbig + 1));
   VI_CUDA_TRY(dalloc(&ctx->fbits, words));
@@ -182,6 +188,7 @@ static int alloc_workspace(vi_ctx* ctx, int64_t n)
   VI_CUDA_TRY(dalloc(&ctx->sub_stats, (size_t)160));
   VI_CUDA_TRY(dalloc((u64**)&ctx->scan_tmp, maxseg / SCAN_TILE + words / SCAN_TILE + 64));
   VI_CUDA_TRY(dalloc(&ctx->gacc, maxbig * ((size_t)ctx->ld * 3 + 3)));
+  VI_CUDA_TRY(dalloc(&ctx->gacc_prev, maxbig * ((size_t)ctx->ld * 3 + 3)));
   VI_CUDA_TRY(dalloc(&ctx->gstats, maxbig * (size_t)ctx->dims));
   VI_CUDA_TRY(dalloc(&ctx->d_absmax, (size_t)4));
   VI_CUDA_TRY(cudaMallocHost((void**)&ctx->totals, sizeof(LevelTotals)));
@@ -331,6 +338,7 @@ struct BuildEnv
 {
   int mode;
   u32 t_team, t_big, big_unroll;
+  u32 sibling;  // fast mode: sum only the smaller child of a big pair, derive the other from the parent (1 = on)
   u32 t_sub;  // ranges of 2..t_sub points are finished by the sub-tree kernel (0 = off)
   u32 sub_minb;
   FastShape shp;      // team / warp-per-range kernels
@@ -377,6 +385,7 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   const u32 t_big_exact = env_u32("VI_B200_T_BIG_EXACT", 512, VI_MIN_BIG, 1u << 30);
   env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
   env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 8, 0, 8);  // 0 = cp.async ring
+  env.sibling = env_u32("VI_B200_SIBLING", 1, 0, 1);
   // sub-tree kernel (fast mode): as many rows as fit 12 KB of shared memory per warp, at most 32 (one point per lane)
   u32 sub_rows = std::min<u32>(32u, (u32)(12288 / (ctx->ld * 4)));
   if (sub_rows < 4 || mode != VI_MODE_FAST || ctx->ld > 128) sub_rows = 0;  // wider rows stay on the level path
@@ -424,7 +433,7 @@ static int local_absmax(vi_ctx* ctx, const float* rows, int64_t n, BuildEnv& env
 
 // launches the fast-mode chunk kernel over the ranges in big_list[cur]
 static void launch_big_fast(vi_ctx* ctx, BuildEnv& env, const float* rows, int cur, u32 nbig, u32 chunks, int mx,
-                            int allow_whole)
+                            int allow_whole, u64* gacc, u32 keep_thr, const u32* bl_sib)
 {
   cudaStream_t st = ctx->stream;
   SegLevel& sg = ctx->seg[cur];
@@ -432,7 +441,7 @@ static void launch_big_fast(vi_ctx* ctx, BuildEnv& env, const float* rows, int c
   const int ld = ctx->ld, dims = ctx->dims;
 #define CALL_BIG_ARGS                                                                                              \
   sg, ctx->big_list[cur], ctx->chunk_first, nbig, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, \
-      sout, ctx->gacc, allow_whole
+      sout, gacc, allow_whole, keep_thr, bl_sib
 #define CALL_BIG(TS, CH, FULL)                                                                                     \
   if (env.big_unroll == 0)                                                                                         \
   {                                                                                                                \
@@ -559,6 +568,16 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
   const FastShape shp = env.shp;
   u32* lvl_counters = ctx->counters + 16;  // u32[16..23]; [2..3] search visits, [4..5] divcheck
 
+  // fast mode: the level's big-list slots and, per slot, whether its sums are derived (sibling derivation)
+  u64 *gacc_cur = ctx->gacc, *gacc_prev = ctx->gacc_prev;
+  bool first_level = true;
+  if (mode == VI_MODE_FAST)
+  {
+    VI_CUDA_TRY(cudaMemsetAsync(ctx->seg[s.cur].bslot, 0xff, (size_t)s.R * sizeof(u32), st));
+    if (s.nbig)
+      k_init_bslot<<<(s.nbig + 255) / 256, 256, 0, st>>>(ctx->seg[s.cur].bslot, s.R, ctx->big_list[s.cur], s.nbig,
+                                                         ctx->bl_parent[s.cur], ctx->bl_sib[s.cur]);
+  }
   while (s.R > 0)
   {
     if (s.level >= VI_MAX_DEPTH)
@@ -575,18 +594,29 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
     {
       if (s.nbig)
       {
-        VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)s.nbig * env.gstride * sizeof(u64), st));
-        launch_big_fast(ctx, env, rows, cur, s.nbig, s.chunks, mx, 1);
-        // ranges that fit one chunk and one column pass were finished by their CTA
-        const int single_pass = (ld / 4) <= env.shp_big.ts * env.shp_big.ch;
-        if (!single_pass || s.maxseg > VI_CHUNK)
+        VI_CUDA_TRY(cudaMemsetAsync(gacc_cur, 0, (size_t)s.nbig * env.gstride * sizeof(u64), st));
+        launch_big_fast(ctx, env, rows, cur, s.nbig, s.chunks, mx, 1, gacc_cur, env.sibling ? 2 * t_big : 0xffffffffu,
+                        env.sibling ? ctx->bl_sib[cur] : nullptr);
+        // sibling derivation: the larger child of a big pair = parent - smaller child (k_emit_children chose them)
+        const bool may_derive = env.sibling && !first_level;
+        if (may_derive)
         {
-          k_finalize_big_fast<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, ctx->gacc, ld,
-                                                                         dims, env.qinv, mx, sout, rows, ctx->perm[cur],
-                                                                         single_pass, 0, nullptr);
+          k_derive_big<<<s.nbig, 256, 0, st>>>(gacc_cur, gacc_prev, ctx->bl_parent[cur], ctx->bl_sib[cur], s.nbig,
+                                               (u32)env.gstride);
           ++env.launches;
         }
+        // ranges that fit one chunk and one column pass were finished by their CTA
+        const int single_pass = (ld / 4) <= env.shp_big.ts * env.shp_big.ch;
+        if (!single_pass || s.maxseg > VI_CHUNK || may_derive)
+        {
+          k_finalize_big_fast<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, gacc_cur, ld,
+                                                                         dims, env.qinv, mx, sout, rows, ctx->perm[cur],
+                                                                         single_pass, 0, nullptr, ctx->bl_parent[cur]);
+          ++env.launches;
+        }
+        std::swap(gacc_cur, gacc_prev);
       }
+      first_level = false;
       // warp-per-range class (teams of a warp share one range); for TS == 32 it also covers the team class
       const u32 wlo = shp.ts == 32 ? 2u : t_team;
       if (s.minseg < t_big && s.maxseg >= wlo)
@@ -702,7 +732,8 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
                                                      row_base_next, (u32)ctx->t_cap, tout, ctx->big_list[nxt], t_big,
                                                      lvl_counters, ctx->c_sub, env.t_sub, s.sub_cnt, s.sub_pos,
                                                      (u32)s.level + 1u, ctx->sub_start, ctx->sub_count, ctx->sub_rid,
-                                                     ctx->sub_row, ctx->sub_depth);
+                                                     ctx->sub_row, ctx->sub_depth, ctx->bl_parent[nxt], ctx->bl_sib[nxt],
+                                                     (mode == VI_MODE_FAST && env.sibling) ? 1 : 0);
     k_scatter<<<(A + 255) / 256, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], A, ctx->fbits,
                                                ctx->wpre, ctx->seg_nlo, ctx->seg_hbase, ctx->c_rows, ctx->c_actpos,
                                                row_base_next, ctx->perm[nxt], ctx->pid[nxt], ctx->seg_of[nxt], ctx->t_id,
@@ -715,7 +746,7 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
     {
       chunk_arr = ctx->chunk_first;
       k_big_chunks<<<(big_bound + 255) / 256, 256, 0, st>>>(ctx->seg[nxt].count, ctx->big_list[nxt], lvl_counters,
-                                                            chunk_arr, big_bound);
+                                                            chunk_arr, big_bound, ctx->bl_parent[nxt]);
       ++env.launches;
       scan_exclusive<u32>(ctx, chunk_arr, big_bound, env.launches);
     }
@@ -950,13 +981,13 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
       return rc;
     // local sums of every range -> gacc, one all-reduce, identical split on every rank
     VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)R * env.gstride * sizeof(u64), st));
-    if (chunks > 0) launch_big_fast(ctx, env, ctx->rows, cur, R, chunks, mx, 0);
+    if (chunks > 0) launch_big_fast(ctx, env, ctx->rows, cur, R, chunks, mx, 0, ctx->gacc, 0xffffffffu, nullptr);
     VI_CUDA_TRY(cudaStreamSynchronize(st));
     if (ctx->allreduce(ctx->coll_user, ctx->gacc, (int64_t)((size_t)R * env.gstride)) != 0)
       return ctx->fail(VI_ERR_CUDA, "all-reduce callback failed");
     VI_CUDA_TRY(cudaMemsetAsync(lvl_counters, 0, 32, st));
     k_finalize_big_fast<<<(R * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], R, ctx->gacc, ld, dims, env.qinv,
-                                                              mx, sout, ctx->rows, ctx->perm[cur], 0, 1, lvl_counters + 1);
+                                                              mx, sout, ctx->rows, ctx->perm[cur], 0, 1, lvl_counters + 1, nullptr);
     ++env.launches;
     cudaEvent_t e1 = env_event(ctx, env);
     // local partition flags and child sizes

@@ -39,6 +39,7 @@ struct SegLevel
   int* dim = nullptr;     // split choice, written by the statistics pass
   float* mid = nullptr;
   i64* pivot = nullptr;
+  u32* bslot = nullptr;   // fast mode: index of the range in the level's big list (its gacc slot), or 0xffffffff
 };
 
 struct LevelTotals  // pinned host, written by the device at the end of every level
@@ -93,6 +94,9 @@ struct vi_ctx
   u32* sub_depth = nullptr;
   u64* sub_stats = nullptr;                 // [64] points + [64] ranges per depth, then the kernel's 2 counters
   void* scan_tmp = nullptr;                 // block sums for scans
+  u64* gacc_prev = nullptr;                 // fast mode: the previous level's gacc (sibling derivation)
+  u32* bl_parent[2] = {nullptr, nullptr};   // per big-list slot: the parent's slot in gacc_prev if the range's sums are
+  u32* bl_sib[2] = {nullptr, nullptr};      //   derived as parent - sibling (bl_sib = the sibling's slot), else 0xffffffff
   u64* gacc = nullptr;                      // fast mode: per big slot [dims][4] + [2] id sums
   float2* gstats = nullptr;                 // exact mode: per big slot [dims] (mean, q)
   u32* counters = nullptr;                  // device counters (nbig_next, ...)

@@ -68,7 +68,7 @@ k_emit_children(SegLevel sg, u32 R, const u32* __restrict__ seg_nlo, const u32* 
                 const u64* __restrict__ c_actpos, SegLevel nx, u32 row_base_next, u32 t_cap, TableOut t,
                 u32* big_list_next, u32 big_thr, u32* counters, const u64* __restrict__ c_sub, u32 t_sub,
                 u32 sub_cnt_base, u32 sub_pos_base, u32 child_depth, u32* sub_start, u32* sub_count, i64* sub_rid,
-                u32* sub_row, u32* sub_depth)
+                u32* sub_row, u32* sub_depth, u32* bl_parent_next, u32* bl_sib_next, int sibling)
 {
   const u32 s = blockIdx.x * 256u + threadIdx.x;
   if ((u64)row_base_next + c_rows[R] > (u64)t_cap)
@@ -87,6 +87,11 @@ k_emit_children(SegLevel sg, u32 R, const u32* __restrict__ seg_nlo, const u32* 
     const u32 b0 = sub_cnt_base + (u32)(c_sub[s] >> 32), q0 = sub_pos_base + (u32)c_sub[s];
     const bool lo_sub = nlo >= 2 && nlo <= t_sub, hi_sub = nhi >= 2 && nhi <= t_sub;
     const bool lo_act = nlo > 1 && !lo_sub;
+    // Sibling derivation (fast mode): when both children are big and the parent's integer sums are in the previous
+    // level's gacc, only the smaller child is summed; the other one's sums are parent - sibling (exact integers).
+    // The pair takes two consecutive big-list slots.
+    const bool pair = sibling && nlo >= big_thr && nhi >= big_thr && sg.bslot[s] != 0xffffffffu;
+    const u32 pair_base = pair ? atomicAdd(&counters[0], 2u) : 0u;
     const int lo_row = nlo > 0 ? (int)r0 : -1;
     const int hi_row = nhi > 0 ? (int)(r0 + (nlo > 0 ? 1u : 0u)) : -1;
     t.t_low[row] = lo_row;
@@ -115,7 +120,22 @@ k_emit_children(SegLevel sg, u32 R, const u32* __restrict__ seg_nlo, const u32* 
         nx.count[a0] = nlo;
         nx.rid[a0] = rid * 2 + 1;
         nx.row[a0] = (u32)lo_row;
-        if (nlo >= big_thr) big_list_next[atomicAdd(&counters[0], 1u)] = a0;
+        u32 slot = 0xffffffffu;
+        if (pair)
+        {
+          slot = pair_base;
+          const bool derived = nlo > nhi;  // the larger one is derived; ties: low is summed
+          bl_parent_next[slot] = derived ? sg.bslot[s] : 0xffffffffu;
+          bl_sib_next[slot] = pair_base + 1u;
+        }
+        else if (nlo >= big_thr)
+        {
+          slot = atomicAdd(&counters[0], 1u);
+          bl_parent_next[slot] = 0xffffffffu;
+          bl_sib_next[slot] = 0xffffffffu;
+        }
+        if (slot != 0xffffffffu) big_list_next[slot] = a0;
+        nx.bslot[a0] = slot;
         cmin = min(cmin, nlo);
         cmax = max(cmax, nlo);
       }
@@ -146,7 +166,22 @@ k_emit_children(SegLevel sg, u32 R, const u32* __restrict__ seg_nlo, const u32* 
         nx.count[a1] = nhi;
         nx.rid[a1] = rid * 2 + 2;
         nx.row[a1] = (u32)hi_row;
-        if (nhi >= big_thr) big_list_next[atomicAdd(&counters[0], 1u)] = a1;
+        u32 slot = 0xffffffffu;
+        if (pair)
+        {
+          slot = pair_base + 1u;
+          const bool derived = nlo <= nhi;
+          bl_parent_next[slot] = derived ? sg.bslot[s] : 0xffffffffu;
+          bl_sib_next[slot] = pair_base;
+        }
+        else if (nhi >= big_thr)
+        {
+          slot = atomicAdd(&counters[0], 1u);
+          bl_parent_next[slot] = 0xffffffffu;
+          bl_sib_next[slot] = 0xffffffffu;
+        }
+        if (slot != 0xffffffffu) big_list_next[slot] = a1;
+        nx.bslot[a1] = slot;
         cmin = min(cmin, nhi);
         cmax = max(cmax, nhi);
       }
@@ -228,13 +263,28 @@ k_scatter(SegLevel sg, const u32* __restrict__ seg_of, const u32* __restrict__ p
   }
 }
 
+// chunk count per big-list slot (a range whose sums are derived from its parent and sibling needs none)
 __global__ void k_big_chunks(const u32* __restrict__ count, const u32* __restrict__ big_list, const u32* counters,
-                             u32* chunks, u32 bound)
+                             u32* chunks, u32 bound, const u32* __restrict__ bl_parent)
 {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= bound) return;
   const u32 nbig = counters[0];
-  chunks[i] = i < nbig ? (count[big_list[i]] + VI_CHUNK - 1) / VI_CHUNK : 0u;
+  const bool summed = i < nbig && (bl_parent == nullptr || bl_parent[i] == 0xffffffffu);
+  chunks[i] = summed ? (count[big_list[i]] + VI_CHUNK - 1) / VI_CHUNK : 0u;
+}
+
+// bslot of a level that did not come out of k_emit_children (the root, the roots of a rank's forest)
+__global__ void k_init_bslot(u32* __restrict__ bslot, u32 R, const u32* __restrict__ big_list, u32 nbig, u32* __restrict__ bl_parent,
+                             u32* __restrict__ bl_sib)
+{
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nbig)
+  {
+    bslot[big_list[i]] = i;
+    bl_parent[i] = 0xffffffffu;
+    bl_sib[i] = 0xffffffffu;
+  }
 }
 
 __global__ void k_totals(const u32* c_rows, const u64* c_actpos, const u64* c_sub, u32 R, const u32* counters,

@@ -291,7 +291,8 @@ template <int TS, int CH, bool FULL, int UNR>
 __global__ void __launch_bounds__(256, (CH == 1) ? 4 : ((TS * CH <= 32) ? 3 : 1))
 k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __restrict__ chunk_first, u32 nbig,
                  const u32* __restrict__ perm, const i64* __restrict__ pid, const float* __restrict__ rows, int ld,
-                 int dims, float qk, double qinv, int mx, StatsOut out, u64* __restrict__ gacc, int allow_whole)
+                 int dims, float qk, double qinv, int mx, StatsOut out, u64* __restrict__ gacc, int allow_whole,
+                 u32 keep_thr, const u32* __restrict__ bl_sib)
 {
   constexpr int NT = 256 / TS;          // teams per CTA
   constexpr int PD = TS * CH * 4;       // dims per pass
@@ -427,6 +428,15 @@ k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __res
     __syncthreads();
     if (whole)
     {
+      // keep the sums: both children may be big (sibling derivation of the next level), or this range's own sibling
+      // is derived from them at this level
+      if (n >= keep_thr || (bl_sib != nullptr && bl_sib[slot] != 0xffffffffu))
+      {
+        const int pd = min(PD, C4 * 4);
+        for (int i = threadIdx.x; i < pd * 3; i += 256) g[i] = sacc[i];
+        if (threadIdx.x < 2) g[(size_t)ld * 3 + threadIdx.x] = sacc[PD * 3 + threadIdx.x];
+        if (threadIdx.x == 2) g[(size_t)ld * 3 + 2] = (u64)n;
+      }
       if (threadIdx.x < 32)
         finalize_big_range(sg, s, n, sacc, sacc + PD * 3, ld, dims, qinv, mx, out, rows, perm, threadIdx.x);
       return;
@@ -444,11 +454,40 @@ k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __res
   if (threadIdx.x == 2) atomicAdd(&g[(size_t)ld * 3 + 2], (u64)m);  // local point count of this chunk
 }
 
-// warp per big range that spans several chunks (or column passes): arg-max over the sums combined in gacc
+// Sibling derivation: sums of a derived range = the parent's (previous level's gacc) - its sibling's (this level's);
+// all words are exact integer sums (S1, the two S2 limbs, the id-sum halves, the count), so the difference is exact.
+__global__ void __launch_bounds__(256)
+k_derive_big(u64* __restrict__ gacc, const u64* __restrict__ gacc_prev, const u32* __restrict__ bl_parent,
+             const u32* __restrict__ bl_sib, u32 nbig, u32 gstride)
+{
+  const u32 slot = blockIdx.x;
+  if (slot >= nbig) return;
+  const u32 par = bl_parent[slot];
+  if (par == 0xffffffffu) return;
+  const u64* gp = gacc_prev + (size_t)par * gstride;
+  const u64* gs = gacc + (size_t)bl_sib[slot] * gstride;
+  u64* g = gacc + (size_t)slot * gstride;
+  const u32 nd = (gstride - 3) / 3;  // = ld
+  for (u32 d = threadIdx.x; d < nd; d += 256)
+  {
+    g[d * 3 + 0] = gp[d * 3 + 0] - gs[d * 3 + 0];  // S1 (two's complement)
+    // S2 = limb0 + limb1 * 2^32; the limbs are sums of 32-bit pieces of the lanes' partial sums, not a canonical
+    // split, so the difference is taken on the 128-bit values and stored as (low 32 bits, the rest)
+    const unsigned __int128 sp = (unsigned __int128)gp[d * 3 + 1] + ((unsigned __int128)gp[d * 3 + 2] << 32);
+    const unsigned __int128 ss = (unsigned __int128)gs[d * 3 + 1] + ((unsigned __int128)gs[d * 3 + 2] << 32);
+    const unsigned __int128 sd = sp - ss;
+    g[d * 3 + 1] = (u64)(sd & 0xffffffffull);
+    g[d * 3 + 2] = (u64)(sd >> 32);
+  }
+  if (threadIdx.x < 3) g[nd * 3 + threadIdx.x] = gp[nd * 3 + threadIdx.x] - gs[nd * 3 + threadIdx.x];  // id sums, count
+}
+
+// warp per big range that spans several chunks (or column passes), or whose sums were derived: arg-max over gacc
 __global__ void __launch_bounds__(256)
 k_finalize_big_fast(SegLevel sg, const u32* __restrict__ big_list, u32 nbig, const u64* __restrict__ gacc, int ld,
                     int dims, double qinv, int mx, StatsOut out, const float* __restrict__ rows,
-                    const u32* __restrict__ perm, int single_pass, int shared, u32* __restrict__ err)
+                    const u32* __restrict__ perm, int single_pass, int shared, u32* __restrict__ err,
+                    const u32* __restrict__ bl_parent)
 {
   const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -458,6 +497,7 @@ k_finalize_big_fast(SegLevel sg, const u32* __restrict__ big_list, u32 nbig, con
   // shared phase of a multi-rank build: n is the all-reduced (global) count and the float32 fallback, which needs
   // the range's rows in global order, is not available: a poorly resolved range is reported as an error
   const u32 n = shared ? (u32)g[(size_t)ld * 3 + 2] : sg.count[s];
-  if (!shared && single_pass && n <= VI_CHUNK) return;  // finished by its chunk CTA
+  const bool derived = bl_parent != nullptr && bl_parent[warp] != 0xffffffffu;
+  if (!shared && single_pass && n <= VI_CHUNK && !derived) return;  // finished by its chunk CTA
   finalize_big_range(sg, s, n, g, g + (size_t)ld * 3, ld, dims, qinv, mx, out, rows, perm, lane, shared ? err : nullptr);
 }
