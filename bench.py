@@ -68,9 +68,13 @@ def peaks():
 
 
 def algorithmic_bytes(levels, dims):
-    """B_l = A_l*(4*D + 28) + R_l*40 per level; statistics kernel alone: A_l*(4*D + 8 + 4)."""
-    whole = sum(l.points * (4 * dims + 28) + l.ranges * 40 for l in levels)
-    stats = sum(l.points * (4 * dims + 12) for l in levels)
+    """B_l = A_l*(4*D + 28) + R_l*40 per level; statistics kernel alone: A_l*(4*D + 8 + 4).
+    Sibling derivation: the rows of a derived range are not part of the statistics pass any more --
+    its sums are parent - sibling -- so those points are charged the partition bytes only; what replaces them is
+    3 x (3*D + 3) x 8 bytes of integer sums per derived range, below 0.1 % and left out."""
+    summed = [l.points - getattr(l, "derived_points", 0) for l in levels]
+    whole = sum(a * (4 * dims + 12) + l.points * 16 + l.ranges * 40 for a, l in zip(summed, levels))
+    stats = sum(a * (4 * dims + 12) for a in summed)
     return whole, stats
 
 
@@ -456,7 +460,7 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum of one k_stats_big_fast launch over 10M x 96 rows from
                 # `ncu --set full` (profiles/r1_ncu_final.md): 3.9606 GB + 4.4 MB for 3.96 GB of algorithmic bytes
                 "traffic": 3.965e9 if (n == 10_000_000 and DIMS == 96) else None,
-                "traffic_note": "per top-level launch (A = 10M points); algorithmic bytes of that launch 3.96e9",
+                "traffic_note": "level-0 launch (A = 10M points, nothing derived); algorithmic bytes of that launch 3.96e9",
                 "algorithmic_bytes_per_launch": stats_b / max(n_stats_launch, 1),
                 "avg_launch_ms": stats_ms / max(n_stats_launch, 1),
                 "whole_build": {"algorithmic_bytes": whole_b, "achieved": whole_b / (ms_per_step / 1e3) / 1e9,
@@ -465,8 +469,9 @@ def main():
                 "subtree_kernel": {"ms": info.subtree_ms, "ranges": int(info.subtree_ranges),
                                    "points_visited": int(sum(l.in_subtrees for l in levels))},
                 "per_level": [{"level": l.level, "ranges": l.ranges, "points": l.points, "in_subtrees": l.in_subtrees,
+                               "derived_points": l.derived_points,
                                "stats_ms": round(l.stats_ms, 4), "partition_ms": round(l.partition_ms, 4),
-                               "stats_gbs": ((l.points - l.in_subtrees) * (4 * DIMS + 12) / (l.stats_ms / 1e3) / 1e9) if l.stats_ms > 0 else None}
+                               "stats_gbs": ((l.points - l.in_subtrees - l.derived_points) * (4 * DIMS + 12) / (l.stats_ms / 1e3) / 1e9) if l.stats_ms > 0 else None}
                               for l in levels]}
     log(f"fast build: {ms_per_step:.2f} ms/step ({[round(x, 2) for x in ms]}), {info.ranges} ranges, {info.levels} levels, "
         f"{info.kernel_launches} launches; stats {stats_ms:.2f} ms (sub-tree kernel {info.subtree_ms:.2f} ms, {info.subtree_ranges} sub-trees) partition {part_ms:.2f} ms")

@@ -65,7 +65,8 @@ typedef struct vi_build_info
 typedef struct vi_level_info
 {
   int32_t level;
-  int32_t reserved;
+  int32_t derived_points; /* of `points`: in big ranges whose integer sums were derived as parent - sibling (fast mode),
+                             i.e. whose rows the statistics pass did not read */
   int64_t ranges;        /* non-leaf ranges processed at this level */
   int64_t points;        /* points in them (A_l) */
   int64_t rows_emitted;  /* table rows created by this level's partition pass */

@@ -354,6 +354,7 @@ struct BuildEnv
 struct LevelState
 {
   u32 A, R, nbig, chunks, minseg, maxseg;
+  u32 derived;   // of A, the points in ranges whose sums are derived rather than summed (fast mode)
   u32 row_next;  // first free table row
   u32 sub_cnt, sub_pos;  // sub-tree list: entries and points so far
   int cur;       // ping-pong index of the current level's buffers
@@ -762,6 +763,7 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
     li.ranges = R;
     li.points = A;
     li.rows_emitted = tt.rows;
+    li.derived_points = (int32_t)s.derived;
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     li.stats_ms = ms;
@@ -777,6 +779,7 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
     s.chunks = tt.chunks;
     s.minseg = tt.minseg;
     s.maxseg = tt.maxseg;
+    s.derived = tt.derived;
     s.sub_cnt += tt.subs;
     s.sub_pos += tt.subpos;
     s.cur = nxt;

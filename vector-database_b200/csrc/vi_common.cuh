@@ -54,6 +54,7 @@ struct LevelTotals  // pinned host, written by the device at the end of every le
   u32 maxseg;
   u32 subs;      // children handed to the sub-tree kernel this level, and their points
   u32 subpos;
+  u32 derived;   // next-level points in ranges whose sums are derived (parent - sibling), fast mode
 };
 
 struct vi_ctx

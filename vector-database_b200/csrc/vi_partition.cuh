@@ -264,14 +264,16 @@ k_scatter(SegLevel sg, const u32* __restrict__ seg_of, const u32* __restrict__ p
 }
 
 // chunk count per big-list slot (a range whose sums are derived from its parent and sibling needs none)
-__global__ void k_big_chunks(const u32* __restrict__ count, const u32* __restrict__ big_list, const u32* counters,
-                             u32* chunks, u32 bound, const u32* __restrict__ bl_parent)
+// counters[6] += points of the derived ranges (accounting: their rows are not read by the statistics pass)
+__global__ void k_big_chunks(const u32* __restrict__ count, const u32* __restrict__ big_list, u32* counters, u32* chunks,
+                             u32 bound, const u32* __restrict__ bl_parent)
 {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= bound) return;
   const u32 nbig = counters[0];
   const bool summed = i < nbig && (bl_parent == nullptr || bl_parent[i] == 0xffffffffu);
   chunks[i] = summed ? (count[big_list[i]] + VI_CHUNK - 1) / VI_CHUNK : 0u;
+  if (i < nbig && !summed) atomicAdd(&counters[6], count[big_list[i]]);
 }
 
 // bslot of a level that did not come out of k_emit_children (the root, the roots of a rank's forest)
@@ -300,6 +302,7 @@ __global__ void k_totals(const u32* c_rows, const u64* c_actpos, const u64* c_su
   out->err = counters[1];
   out->minseg = counters[4];
   out->maxseg = counters[5];
+  out->derived = counters[6];
 }
 
 __global__ void k_pack_nodes(const int* __restrict__ t_dim, const float* __restrict__ t_mid, const i64* __restrict__ t_id,

@@ -43,7 +43,7 @@ class BuildInfo(ctypes.Structure):
 
 
 class LevelInfo(ctypes.Structure):
-    _fields_ = [("level", ctypes.c_int32), ("reserved", ctypes.c_int32), ("ranges", ctypes.c_int64),
+    _fields_ = [("level", ctypes.c_int32), ("derived_points", ctypes.c_int32), ("ranges", ctypes.c_int64),
                 ("points", ctypes.c_int64), ("rows_emitted", ctypes.c_int64), ("stats_ms", ctypes.c_double),
                 ("partition_ms", ctypes.c_double), ("in_subtrees", ctypes.c_int64)]
 
