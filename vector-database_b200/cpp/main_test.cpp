@@ -3,6 +3,7 @@
 // rows (Program.cs:80 CSV shape) so a test can diff them against the oracle.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 
 #include "vector_index.hpp"
@@ -28,6 +29,17 @@ int main(int argc, char** argv)
       uint32_t bits;
       memcpy(&bits, &range.Mid, 4);
       printf("%lld,%d,%u,%lld\n", (long long)rangeId, range.Dimension, bits, (long long)range.Id);
+    }
+    // the rows alone are a searchable index (vi_ranges_load): a point lookup at proximity 0 must return the point
+    RangeIndex lookup(index, dimensions);
+    for (int64_t i = 0; i < dimensions && i < 16; ++i)
+    {
+      const std::vector<int64_t> ids = lookup.Search(input[(size_t)i].second, 0.0f);
+      if (std::find(ids.begin(), ids.end(), i) == ids.end())
+      {
+        fprintf(stderr, "error: point %lld not found by the imported table\n", (long long)i);
+        return 2;
+      }
     }
   }
   catch (const std::exception& e)

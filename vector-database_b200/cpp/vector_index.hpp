@@ -112,4 +112,42 @@ class IndexBuilder
     return out;
   }
 };
+
+// The consumer side of Program.cs:18-26: the rows a caller collected (or read back from the CSV of
+// Program.cs:145-149) become a searchable index again (vi_ranges_load), and Search is dbo.Search (DDL.sql:234-295).
+class RangeIndex
+{
+ public:
+  RangeIndex(const std::vector<std::pair<int64_t, RangeValue>>& rows, int32_t dimensions, int device = 0)
+      : ctx_(MakeContext(device)), dims_(dimensions)
+  {
+    std::vector<int64_t> rid, oid;
+    std::vector<int32_t> dim;
+    std::vector<float> mid;
+    for (auto& [r, v] : rows)
+    {
+      rid.push_back(r);
+      dim.push_back(v.Dimension);
+      mid.push_back(v.Mid);
+      oid.push_back(v.Id);
+    }
+    Check(ctx_.get(), vi_ranges_load(ctx_.get(), rid.data(), dim.data(), mid.data(), oid.data(), (int64_t)rid.size(), dims_));
+  }
+
+  // candidate ids of one query, traversal order (low branch first)
+  std::vector<int64_t> Search(const std::vector<float>& vector, float proximity) const
+  {
+    if ((int32_t)vector.size() != dims_) throw std::invalid_argument("Invalid vector size.");  // MemoryVectorIndex.cs:254
+    int64_t offsets[2] = {0, 0}, total = 0;
+    Check(ctx_.get(), vi_search(ctx_.get(), vector.data(), 1, dims_, proximity, offsets, nullptr, 0, &total));
+    std::vector<int64_t> ids((size_t)total);
+    if (total > 0)
+      Check(ctx_.get(), vi_search(ctx_.get(), vector.data(), 1, dims_, proximity, offsets, ids.data(), total, &total));
+    return ids;
+  }
+
+ private:
+  CtxPtr ctx_;
+  int32_t dims_;
+};
 }  // namespace NesterovskyBros::VectorIndex
