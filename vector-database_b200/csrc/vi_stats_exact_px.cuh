@@ -1,11 +1,12 @@
 // vi_stats_exact_px.cuh -- exact-mode statistics of the TOP levels: the literal float32 recurrence of
-// IndexBuilder.cs:159-197 for one (range, 32 dimensions) per CTA, split over five specialised warps.
+// IndexBuilder.cs:159-197 for one (range, 32 dimensions) per CTA, split over six specialised warps.
 //
 // Why: at the top of the tree there are only ranges x dims/32 chains-of-warps in the whole GPU and each is one serial
 // dependency over up to N points, so the build time is (cycles per step) x N.  One warp issues at most one
 // instruction every 2 cycles; the single-warp kernel (k_stats_big_exact, ~19 instructions per step) is therefore
 // issue-bound at ~37-45 cycles per step although its dependency chain is 16-18.  Here the warp that owns the chain
-// executes only the chain (7 instructions per step) and four other warps do the rest:
+// executes only the chain (LDS v, LDS.64 r, FADD, FMUL, FFMA, FADD per step + a STS.128 per four steps) and five other
+// warps do the rest:
 //
 //   warp 5,6  loaders   (even / odd groups) row indexes + 16-byte cp.async row copies into the row ring,
 //                       (RN(1/c), lo(1/c), c) tables; warps 4 and 7 exit at once, so that the chain warp has its
@@ -15,11 +16,15 @@
 //   warp 3    variance  q_k = q_{k-1} + (v - mean_{k-1})*(v - mean_k), tiny-operand guard; owns the committed state
 //
 // Groups of 32 points flow loader -> chain -> verifier -> variance through shared-memory rings; progress counters
-// (one writer each) are published with a CTA fence every PX_K groups (a fence costs ~100 cycles) and polled.  A group a
-// verifier or the guard rejects (about one in 10^4: the speculative quotient was not RN(d/c)) triggers a restart: the
-// four compute warps meet at a named barrier, the variance warp -- whose (mean, q) is the state after the last group
-// it committed -- redoes the groups up to the rejected one with welford_step_r (Markstein / IEEE division), and
-// everybody resumes behind it.  The result is bit-identical to the sequential recurrence.
+// (one writer each) are release stores / acquire loads at CTA scope (the release costs a MEMBAR that waits for the
+// warp's stores in flight, so the chain publishes once per PX_K groups) and are polled.  A group a verifier or the
+// guard rejects (about one in 10^4: the speculative quotient was not RN(d/c)) triggers a restart: the four compute
+// warps meet at a named barrier, the variance warp -- whose (mean, q) is the state after the last group it committed
+// -- redoes the groups up to the rejected one with welford_step_r (Markstein / IEEE division), and everybody resumes
+// behind it; after 16 restarts (NaN-poisoned or denormal data) it finishes the range alone.  The result is
+// bit-identical to the sequential recurrence.  Liveness: every wait polls the restart flag, every warp that can be
+// waited on stays until the variance warp has committed the last full group, and a warp never waits for a group that
+// needs its own unpublished output.
 #pragma once
 #include "vi_stats_exact.cuh"
 
