@@ -39,6 +39,12 @@ KATS = [
      "ids": [1, 2, 3, 4], "rows": [[0.0, 1.0], [0.0, 1.0], [4.0, 1.0], [4.0, 1.0]],
      "table": {"0": [0, 2.0, 2], "1": [0, 0.0, 1], "2": [0, 4.0, 3], "3": [-1, 0.0, 1], "4": [-1, 0.0, 2],
                "5": [-1, 0.0, 3], "6": [-1, 0.0, 4]}},
+    {"name": "odd depth picks the SMALLER non-zero variance: root (even) splits dim 0 (values 0,6,12,18: the float32 "
+             "recurrence is exact here, mean 3 -> 6 -> 9, q 18 -> 72 -> 180; Id trunc(10/4) = 2); each child holds two "
+             "points with q = 18 in dim 0 and (0.5)(0.25) = 0.125 in dim 1, so the min-variance level splits dim 1 at 0.25",
+     "ids": [1, 2, 3, 4], "rows": [[0.0, 0.0], [6.0, 0.5], [12.0, 0.0], [18.0, 0.5]],
+     "table": {"0": [0, 9.0, 2], "1": [1, 0.25, 1], "2": [1, 0.25, 3], "3": [-1, 0.0, 1], "4": [-1, 0.0, 2],
+               "5": [-1, 0.0, 3], "6": [-1, 0.0, 4]}},
 ]
 
 SEARCH_KAT = {
