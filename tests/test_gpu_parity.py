@@ -498,3 +498,13 @@ def test_topk_recall_reaches_one_when_the_box_covers_the_neighbours():
     assert np.all(cnt == k)
     for i in range(len(q)):
         assert set(got_ids[i].tolist()) == set(ids[exact[i]].tolist())
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_one_million_points_bit_exact(mode):
+    # 1M x 96: 20+ levels -- the exact mode's pipeline kernel on six levels, the fast mode's sibling derivation on
+    # ten, every range class and ~47 k sub-trees -- against the oracle row for row (the largest size the oracle
+    # finishes in seconds; beyond it tests/test_gpu_fullsize.py checks properties)
+    ids, rows = ds.unit_gaussian(1_000_000, 96, seed=61)
+    info = assert_same_table(ids, rows, mode)
+    assert info.levels >= 20
