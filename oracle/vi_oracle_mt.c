@@ -142,12 +142,14 @@ int vio_build_mt(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
   float* mean = (float*)malloc((size_t)d * 4);
   float* q = (float*)malloc((size_t)d * 4);
   rows_t* outs = (rows_t*)calloc((size_t)threads + 1, sizeof(rows_t));
+  const size_t dpad = ((size_t)d + 31) & ~(size_t)31; /* 128-byte multiples */
+  float* priv = (float*)aligned_alloc(128, (size_t)threads * 2 * dpad * 4);
   int64_t tcap = 65536, ntask = 0, nopen = 1;
   range_t* tasks = (range_t*)malloc((size_t)tcap * sizeof(range_t));
   range_t* open_ = (range_t*)malloc((size_t)tcap * sizeof(range_t));
   range_t* next = (range_t*)malloc((size_t)tcap * sizeof(range_t));
   int rc = 0, overflow = 0, fail = 0;
-  if (!perm || !tmp || !mean || !q || !outs || !tasks || !open_ || !next) { rc = -3; goto done; }
+  if (!perm || !tmp || !mean || !q || !outs || !tasks || !open_ || !next || !priv) { rc = -3; goto done; }
   for (int64_t i = 0; i < n; ++i) perm[i] = i;
   open_[0] = (range_t){0, 0, n, 1};
   /* top of the tree: ranges too big to hand to one thread -> threads split the dimensions */
@@ -167,9 +169,18 @@ int vio_build_mt(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
       }
 #pragma omp parallel
       {
+        /* every thread keeps its chains in its own cache-line-aligned block (the shared mean[]/q[] would put the
+         * slices of neighbouring threads on one line: false sharing on every step) and publishes them once */
         const int t = omp_get_thread_num(), T = omp_get_num_threads();
         const int32_t d0 = (int32_t)((int64_t)d * t / T), d1 = (int32_t)((int64_t)d * (t + 1) / T);
-        if (d1 > d0) welford_dims(rows, ld, perm + it.start, it.count, d0, d1, mean, q);
+        if (d1 > d0)
+        {
+          float* pm = priv + (size_t)t * 2 * dpad;
+          float* pq = pm + dpad;
+          welford_dims(rows, ld, perm + it.start, it.count, d0, d1, pm, pq);
+          memcpy(mean + d0, pm + d0, (size_t)(d1 - d0) * 4);
+          memcpy(q + d0, pq + d0, (size_t)(d1 - d0) * 4);
+        }
       }
       range_t lo, hi;
       if (!finish_range(rows, ld, d, ids, perm, tmp, it, mean, q, &outs[threads], &lo, &hi, &overflow)) { fail = 1; break; }
@@ -234,6 +245,6 @@ int vio_build_mt(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
 done:
   if (outs)
     for (int t = 0; t <= threads; ++t) { free(outs[t].rid); free(outs[t].dim); free(outs[t].mid); free(outs[t].id); }
-  free(outs); free(perm); free(tmp); free(mean); free(q); free(tasks); free(open_); free(next);
+  free(outs); free(perm); free(tmp); free(mean); free(q); free(tasks); free(open_); free(next); free(priv);
   return rc;
 }

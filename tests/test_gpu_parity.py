@@ -73,6 +73,14 @@ def test_wide_rows_768(mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
+def test_config5_width_200k_x_768(mode):
+    # BASELINE configs[4] (1M x 768) at a size the oracle finishes in seconds: every range class at the full row width
+    ids, rows = ds.unit_gaussian(200_000, 768, seed=31)
+    info = assert_same_table(ids * 5 - 17, rows, mode)
+    assert info.ranges >= 2 * 200_000 - 1
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_one_hot_crafted_set(mode):
     # Program.cs:54-66; literal mode must pick dimension 3 at the root, qfx dimension 0
     ids, rows = ds.one_hot(1536)
@@ -174,6 +182,30 @@ def test_search_matches_oracle_traversal(p):
     if p == 0.0:
         for i in range(300):
             assert ids[i] in out[offs[i]:offs[i + 1]]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_search_csr_parity_on_1m_point_index(mode):
+    # a table with sub-tree blocks, one-child rows and 21+ levels: CSR arrays (not only sets) equal the oracle's
+    n = 1_000_000
+    ids, rows = ds.unit_gaussian(n, 96, seed=2)
+    _, fresh = ds.unit_gaussian(500, 96, seed=78)
+    queries = np.concatenate([rows[:250], rows[n - 250:], fresh], 0)
+    ref = oracle.build(ids, rows, mode)
+    with vi.Context(0) as ctx:
+        ctx.reserve(n, 96)
+        ctx.add(ids, rows)
+        ctx.build(mode)
+        for p in (0.0, 0.01, 0.03):
+            offs, out = ctx.search(queries, p)
+            roffs, rout, _ = oracle.search(ref, queries, p)
+            assert np.array_equal(offs, roffs)
+            assert np.array_equal(out, rout)
+        # p = 0 finds every data point that is queried
+        offs, out = ctx.search(queries[:500], 0.0)
+        want = np.concatenate([ids[:250], ids[n - 250:]])
+        for i in range(500):
+            assert want[i] in out[offs[i]:offs[i + 1]]
 
 
 def test_search_verify_equals_bruteforce():

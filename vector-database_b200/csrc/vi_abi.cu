@@ -95,9 +95,16 @@ static int reserve_points(vi_ctx* ctx, int64_t capacity)
   if (e != cudaSuccess) { cudaFree(nrows); return ctx->fail_cuda(e, "cudaMalloc(ids)", __FILE__, __LINE__); }
   if (ctx->n > 0)
   {
-    cudaMemcpyAsync(nrows, ctx->rows, (size_t)ctx->n * ctx->ld * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
-    cudaMemcpyAsync(nids, ctx->ids, (size_t)ctx->n * sizeof(i64), cudaMemcpyDeviceToDevice, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
+    e = cudaMemcpyAsync(nrows, ctx->rows, (size_t)ctx->n * ctx->ld * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(nids, ctx->ids, (size_t)ctx->n * sizeof(i64), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess)
+    {
+      cudaFree(nrows);  // the old store stays valid
+      cudaFree(nids);
+      return ctx->fail_cuda(e, "growing the point store", __FILE__, __LINE__);
+    }
   }
   cudaFree(ctx->rows);
   cudaFree(ctx->ids);
@@ -300,11 +307,22 @@ int vi_textindex_copy(const vi_ctx* cctx, int64_t* range_id, int16_t* dimension,
   return VI_OK;
 }
 
+static int searchable(vi_ctx* ctx)
+{
+  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  // after a multi-rank build a context holds the shared top rows plus its own sub-trees; the level-L rows of ranges
+  // owned elsewhere are Dimension == -2 placeholders without Id / Mid / source row: not a searchable table
+  if (ctx->world > 1 && !ctx->replicated)
+    return ctx->fail(VI_ERR_STATE, "multi-rank build: call vi_table_replicate before searching (this rank holds only "
+                                   "the sub-trees it owns)");
+  return VI_OK;
+}
+
 int vi_search_device(vi_ctx* ctx, const float* d_queries, int64_t nq, int32_t dims, float proximity, int64_t* d_offsets,
                      int64_t* d_ids, int64_t cap, int64_t* total, int64_t* visits)
 {
   if (!ctx || !total) return VI_ERR_INVALID_ARG;
-  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  { const int rs = searchable(ctx); if (rs != VI_OK) return rs; }
   if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");  // MemoryVectorIndex.cs:254
   if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !d_queries) || !d_offsets)
     return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
@@ -332,7 +350,7 @@ int vi_search(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float
               int64_t* ids, int64_t cap, int64_t* total)
 {
   if (!ctx || !total || !offsets) return VI_ERR_INVALID_ARG;
-  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  { const int rs = searchable(ctx); if (rs != VI_OK) return rs; }
   if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");
   if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !queries)) return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
   VI_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -369,11 +387,12 @@ int vi_search_topk(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, 
                    int64_t* ids, float* dist, int32_t* count, int64_t* candidates)
 {
   if (!ctx) return VI_ERR_INVALID_ARG;
-  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  { const int rs = searchable(ctx); if (rs != VI_OK) return rs; }
   if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");
   if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !queries)) return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
   if (k <= 0 || k > 1024 || (metric != 0 && metric != 1)) return ctx->fail(VI_ERR_INVALID_ARG, "k must be 1..1024, metric 0 or 1");
-  if (ctx->replicated) return ctx->fail(VI_ERR_STATE, "top-k needs the vectors: not on a replicated or imported table");
+  if (ctx->replicated || !ctx->src_rows)
+    return ctx->fail(VI_ERR_STATE, "top-k needs the vectors: not on a replicated or imported table");
   VI_CUDA_TRY(cudaSetDevice(ctx->device));
   int rc = stage_queries(ctx, queries, nq);
   if (rc != VI_OK) return rc;
@@ -384,16 +403,17 @@ int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims
                      int64_t* offsets, int64_t* ids, int64_t cap, int64_t* total)
 {
   if (!ctx || !total || !offsets) return VI_ERR_INVALID_ARG;
-  if (!ctx->built) return ctx->fail(VI_ERR_STATE, "no built index");
+  { const int rs = searchable(ctx); if (rs != VI_OK) return rs; }
   if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");
   if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !queries)) return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
   VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (ctx->replicated || !ctx->src_rows)
+    return ctx->fail(VI_ERR_STATE, "candidate verification needs the vectors: not on a replicated or imported table");
   int rc = stage_queries(ctx, queries, nq);
   if (rc != VI_OK) return rc;
   int64_t cand = 0;
   int* keep_src = ctx->search_src;
   ctx->search_src = nullptr;
-  if (ctx->replicated) return ctx->fail(VI_ERR_STATE, "candidate verification needs the vectors: not on a replicated or imported table");
   rc = vi_search_impl(ctx, ctx->q_buf, nq, proximity, ctx->off_buf, nullptr, 0, &cand, nullptr, false);
   ctx->search_src = keep_src;
   if (rc != VI_OK) return rc;

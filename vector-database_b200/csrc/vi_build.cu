@@ -101,16 +101,18 @@ void vi_free_workspace(vi_ctx* ctx)
     s = SegLevel();
     cudaFree(ctx->bl_parent[i]); ctx->bl_parent[i] = nullptr;
     cudaFree(ctx->bl_sib[i]); ctx->bl_sib[i] = nullptr;
+    cudaFree(ctx->chunk_first[i]); ctx->chunk_first[i] = nullptr;
   }
-  cudaFree(ctx->chunk_first); ctx->chunk_first = nullptr;
   cudaFree(ctx->fbits); ctx->fbits = nullptr;
-  cudaFree(ctx->wpre); ctx->wpre = nullptr;
+  cudaFree(ctx->wloc); ctx->wloc = nullptr;
+  cudaFree(ctx->ftile); ctx->ftile = nullptr;
   cudaFree(ctx->seg_nlo); ctx->seg_nlo = nullptr;
   cudaFree(ctx->seg_hbase); ctx->seg_hbase = nullptr;
-  cudaFree(ctx->c_rows); ctx->c_rows = nullptr;
-  cudaFree(ctx->c_actpos); ctx->c_actpos = nullptr;
+  cudaFree(ctx->c_pre); ctx->c_pre = nullptr;
+  cudaFree(ctx->ctile); ctx->ctile = nullptr;
+  cudaFree(ctx->ctile_mm); ctx->ctile_mm = nullptr;
+  cudaFree(ctx->lv); ctx->lv = nullptr;
   cudaFree(ctx->scan_tmp); ctx->scan_tmp = nullptr;
-  cudaFree(ctx->c_sub); ctx->c_sub = nullptr;
   cudaFree(ctx->sub_perm); ctx->sub_perm = nullptr;
   cudaFree(ctx->sub_pid); ctx->sub_pid = nullptr;
   cudaFree(ctx->sub_start); ctx->sub_start = nullptr;
@@ -123,8 +125,8 @@ void vi_free_workspace(vi_ctx* ctx)
   cudaFree(ctx->gacc_prev); ctx->gacc_prev = nullptr;
   cudaFree(ctx->gstats); ctx->gstats = nullptr;
   cudaFree(ctx->d_absmax); ctx->d_absmax = nullptr;
-  if (ctx->totals) cudaFreeHost(ctx->totals);
-  ctx->totals = nullptr;
+  if (ctx->h_lv) cudaFreeHost(ctx->h_lv);
+  ctx->h_lv = nullptr;
   ctx->ws_n = 0;
 }
 
@@ -151,7 +153,7 @@ static int alloc_workspace(vi_ctx* ctx, int64_t n)
   // lower bounds: the multi-rank build uses these arrays as scratch for its (small) host-built tables
   const size_t maxseg = std::max<size_t>(N / 2 + 2, 65536);
   const size_t maxbig = std::max<size_t>(N / VI_MIN_BIG + 2, 256);
-  const size_t words = N / 32 + 4;
+  const size_t words = (N / FL_TILE + 2) * FL_WORDS;  // whole flag tiles, position N included
   for (int i = 0; i < 2; ++i)
   {
     VI_CUDA_TRY(dalloc(&ctx->perm[i], N));
@@ -169,15 +171,17 @@ static int alloc_workspace(vi_ctx* ctx, int64_t n)
     VI_CUDA_TRY(dalloc(&s.bslot, maxseg));
     VI_CUDA_TRY(dalloc(&ctx->bl_parent[i], maxbig));
     VI_CUDA_TRY(dalloc(&ctx->bl_sib[i], maxbig));
+    VI_CUDA_TRY(dalloc(&ctx->chunk_first[i], maxbig + 1));
   }
-  VI_CUDA_TRY(dalloc(&ctx->chunk_first, maxbig + 1));
   VI_CUDA_TRY(dalloc(&ctx->fbits, words));
-  VI_CUDA_TRY(dalloc(&ctx->wpre, words + 1));
+  VI_CUDA_TRY(dalloc(&ctx->wloc, words));
+  VI_CUDA_TRY(dalloc(&ctx->ftile, N / FL_TILE + 8));
   VI_CUDA_TRY(dalloc(&ctx->seg_nlo, maxseg));
   VI_CUDA_TRY(dalloc(&ctx->seg_hbase, maxseg));
-  VI_CUDA_TRY(dalloc(&ctx->c_rows, maxseg + 1));
-  VI_CUDA_TRY(dalloc(&ctx->c_actpos, maxseg + 1));
-  VI_CUDA_TRY(dalloc(&ctx->c_sub, maxseg + 1));
+  VI_CUDA_TRY(dalloc(&ctx->c_pre, maxseg));
+  VI_CUDA_TRY(dalloc(&ctx->ctile, maxseg / CH_TILE + 8));
+  VI_CUDA_TRY(dalloc(&ctx->ctile_mm, maxseg / CH_TILE + 8));
+  VI_CUDA_TRY(dalloc(&ctx->lv, (size_t)VI_LV_N));
   VI_CUDA_TRY(dalloc(&ctx->sub_perm, N));
   VI_CUDA_TRY(dalloc(&ctx->sub_pid, N));
   VI_CUDA_TRY(dalloc(&ctx->sub_start, maxseg));
@@ -191,7 +195,7 @@ static int alloc_workspace(vi_ctx* ctx, int64_t n)
   VI_CUDA_TRY(dalloc(&ctx->gacc_prev, maxbig * ((size_t)ctx->ld * 3 + 3)));
   VI_CUDA_TRY(dalloc(&ctx->gstats, maxbig * (size_t)ctx->dims));
   VI_CUDA_TRY(dalloc(&ctx->d_absmax, (size_t)4));
-  VI_CUDA_TRY(cudaMallocHost((void**)&ctx->totals, sizeof(LevelTotals)));
+  VI_CUDA_TRY(cudaMallocHost((void**)&ctx->h_lv, sizeof(LevelDev) * VI_LV_N));
   ctx->ws_n = n;
   return VI_OK;
 }
@@ -339,8 +343,9 @@ struct BuildEnv
   int mode;
   u32 t_team, t_big, big_unroll;
   u32 sibling;  // fast mode: sum only the smaller child of a big pair, derive the other from the parent (1 = on)
-  u32 t_sub;  // ranges of 2..t_sub points are finished by the sub-tree kernel (0 = off)
+  u32 t_sub;    // ranges of 2..t_sub points are finished by the sub-tree kernel (0 = off)
   u32 sub_minb;
+  u32 lag;      // levels the host may run ahead of the last level record it has read back (1 = none)
   FastShape shp;      // team / warp-per-range kernels
   FastShape shp_big;  // chunk kernel
   int chx;
@@ -351,13 +356,14 @@ struct BuildEnv
   std::vector<cudaEvent_t> ev;
 };
 
+// Host-side copy of a level record (exact once the device's copy has been read back).
 struct LevelState
 {
   u32 A, R, nbig, chunks, minseg, maxseg;
   u32 derived;   // of A, the points in ranges whose sums are derived rather than summed (fast mode)
   u32 row_next;  // first free table row
   u32 sub_cnt, sub_pos;  // sub-tree list: entries and points so far
-  int cur;       // ping-pong index of the current level's buffers
+  int cur;       // ping-pong index of the level's buffers
   int level;     // depth of the ranges in seg[cur]
 };
 
@@ -392,6 +398,10 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   if (sub_rows < 4 || mode != VI_MODE_FAST || ctx->ld > 128) sub_rows = 0;  // wider rows stay on the level path
   env.t_sub = std::min(env_u32("VI_B200_T_SUB", sub_rows, 0, 32), sub_rows);
   env.sub_minb = env_u32("VI_B200_SUB_MINB", 2, 2, 3);
+  // The host enqueues level l+1 before it has read level l's record back (the kernels take their sizes from the
+  // device-resident record, the grids from bounds derived from the last record the host knows).  The exact mode's
+  // kernels are launched on exact sizes (its top levels are latency-bound chains anyway): no run-ahead there.
+  env.lag = mode == VI_MODE_FAST ? env_u32("VI_B200_LAG", 2, 1, 4) : 1u;
   // Rows up to 128 floats wide: the chunk kernel reads a row with ONE float4 per lane of a whole warp (lanes beyond
   // the row idle): 16 accumulator registers per lane instead of 48, 63 registers, unroll 8 -> 0.72 ms per 10M x 96
   // level instead of 0.90 (profiles/r1_sweep.txt).  The small-range kernels keep 8-lane teams (bit 1 switches them).
@@ -432,16 +442,18 @@ static int local_absmax(vi_ctx* ctx, const float* rows, int64_t n, BuildEnv& env
   return VI_OK;
 }
 
-// launches the fast-mode chunk kernel over the ranges in big_list[cur]
-static void launch_big_fast(vi_ctx* ctx, BuildEnv& env, const float* rows, int cur, u32 nbig, u32 chunks, int mx,
-                            int allow_whole, u64* gacc, u32 keep_thr, const u32* bl_sib)
+// launches the fast-mode chunk kernel over the ranges in big_list[cur]; `chunks_bound` >= the level's chunk count
+// (the kernel reads the count from the level record `lvp` and surplus CTAs exit)
+static void launch_big_fast(vi_ctx* ctx, BuildEnv& env, const LevelDev* lvp, const float* rows, int cur, u32 chunks_bound,
+                            int mx, int allow_whole, u64* gacc, u32 keep_thr, const u32* bl_sib)
 {
   cudaStream_t st = ctx->stream;
   SegLevel& sg = ctx->seg[cur];
   StatsOut sout{ctx->t_dim, ctx->t_mid, ctx->t_id};
   const int ld = ctx->ld, dims = ctx->dims;
+  const u32 chunks = chunks_bound;
 #define CALL_BIG_ARGS                                                                                              \
-  sg, ctx->big_list[cur], ctx->chunk_first, nbig, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, \
+  lvp, sg, ctx->big_list[cur], ctx->chunk_first[cur], ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, \
       sout, gacc, allow_whole, keep_thr, bl_sib
 #define CALL_BIG(TS, CH, FULL)                                                                                     \
   if (env.big_unroll == 0)                                                                                         \
@@ -556,240 +568,305 @@ static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* 
   return VI_OK;
 }
 
-// The level loop: processes seg[s.cur] (ranges of depth s.level) until no range with >= 2 points is left.
-// `rows` is the row store perm[] indexes.
-static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* rows)
+static LevelDev lv_from_state(const LevelState& s)
+{
+  LevelDev v{};
+  v.A = s.A;
+  v.R = s.R;
+  v.nbig = s.nbig;
+  v.chunks = s.chunks;
+  v.minseg = s.minseg;
+  v.maxseg = s.maxseg;
+  v.derived = s.derived;
+  v.row_next = s.row_next;
+  v.sub_cnt = s.sub_cnt;
+  v.sub_pos = s.sub_pos;
+  return v;
+}
+
+// Puts the first level record of a level loop on the device (all later ones are written by k_children).
+static int upload_level(vi_ctx* ctx, const LevelState& s)
+{
+  cudaStream_t st = ctx->stream;
+  VI_CUDA_TRY(cudaMemsetAsync(ctx->lv, 0, sizeof(LevelDev) * VI_LV_N, st));  // tickets of every level start at 0
+  ctx->h_lv[s.level] = lv_from_state(s);  // pinned staging: stays untouched until the copy has run (end of the build)
+  VI_CUDA_TRY(cudaMemcpyAsync(ctx->lv + s.level, ctx->h_lv + s.level, sizeof(LevelDev), cudaMemcpyHostToDevice, st));
+  return VI_OK;
+}
+
+// One level's launches.  `b` holds bounds on the level's sizes (exact when lag == 1); the kernels read the real sizes
+// from lv[level].
+struct LevelEvents
+{
+  cudaEvent_t e0, e1, e2;
+};
+
+static int enqueue_level(vi_ctx* ctx, BuildEnv& env, const LevelState& b, int level, int cur, bool exact_sizes,
+                         bool first_level, const float* rows, u64* gacc_cur, u64* gacc_prev, LevelEvents& ev)
 {
   cudaStream_t st = ctx->stream;
   const int ld = ctx->ld, dims = ctx->dims;
   const int mode = env.mode;
+  const int nxt = cur ^ 1;
+  const int mx = (level & 1) == 0;  // root max = true, children !max (IndexBuilder.cs:33,128-129)
+  SegLevel& sg = ctx->seg[cur];
   TableOut tout{ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high};
   StatsOut sout{ctx->t_dim, ctx->t_mid, ctx->t_id};
   const u32 t_team = env.t_team, t_big = env.t_big;
   const FastShape shp = env.shp;
-  u32* lvl_counters = ctx->counters + 16;  // u32[16..23]; [2..3] search visits, [4..5] divcheck
+  LevelDev* lvp = ctx->lv + level;
+  ev.e0 = env_event(ctx, env);
 
+  // ---- statistics + split choice ---------------------------------------------------------------------------
+  if (mode == VI_MODE_FAST)
+  {
+    if (b.nbig)
+    {
+      VI_CUDA_TRY(cudaMemsetAsync(gacc_cur, 0, (size_t)b.nbig * env.gstride * sizeof(u64), st));
+      launch_big_fast(ctx, env, lvp, rows, cur, b.chunks, mx, 1, gacc_cur, env.sibling ? 2 * t_big : 0xffffffffu,
+                      env.sibling ? ctx->bl_sib[cur] : nullptr);
+      // derived ranges (parent - sibling), ranges that span several chunks or column passes: split choice from gacc;
+      // ranges that fit one chunk and one column pass were finished by their CTA
+      const int single_pass = (ld / 4) <= env.shp_big.ts * env.shp_big.ch;
+      if (!single_pass || b.maxseg > VI_CHUNK || env.sibling)
+      {
+        k_finalize_big_fast<<<(b.nbig * 32 + 255) / 256, 256, 0, st>>>(
+            lvp, sg, ctx->big_list[cur], gacc_cur, gacc_prev, ld, dims, env.qinv, mx, sout, rows, ctx->perm[cur], single_pass,
+            0, nullptr, env.sibling ? ctx->bl_parent[cur] : nullptr, ctx->bl_sib[cur]);
+        ++env.launches;
+      }
+    }
+    // warp-per-range class (teams of a warp share one range); for TS == 32 it also covers the team class.
+    // Below the first level of a loop every range has more than t_sub points (smaller children went to the sub-tree
+    // list); the first level's ranges (the root, the roots of a rank's forest) can have any size.
+    const u32 floor_n = first_level ? 2u : env.t_sub + 1u;
+    const u32 wlo = shp.ts == 32 ? 2u : t_team;
+    const bool may_warp = std::max(wlo, floor_n) < t_big && b.maxseg >= wlo && (!exact_sizes || b.minseg < t_big);
+    if (may_warp)
+    {
+#define CALL_WARP(TS, CH, FULL)                                                                              \
+  k_stats_small_fast<TS, CH, FULL, true><<<(u32)(((u64)b.R * 32 + 255) / 256), 256, 0, st>>>(                 \
+      lvp, sg, wlo, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout)
+      FAST_DISPATCH(shp, CALL_WARP);
+#undef CALL_WARP
+      ++env.launches;
+    }
+    const bool may_team = shp.ts < 32 && floor_n < t_team && (!exact_sizes || b.minseg < t_team);
+    if (may_team)
+    {
+#define CALL_TEAM(TS, CH, FULL)                                                                              \
+  k_stats_small_fast<TS, CH, FULL, false><<<(u32)(((u64)b.R * TS + 255) / 256), 256, 0, st>>>(                \
+      lvp, sg, 2u, t_team, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout)
+      FAST_DISPATCH(shp, CALL_TEAM);
+#undef CALL_TEAM
+      ++env.launches;
+    }
+  }
+  else
+  {
+    // exact mode: `b` is exact (lag == 1)
+    if (b.nbig)
+    {
+      const u32 nblk = (u32)((dims + 31) / 32);
+      const bool vec_ok = ld % 4 == 0 && ((uintptr_t)rows & 15) == 0;
+      // top levels (few chains in the whole GPU): the warp-specialised pipeline, vi_stats_exact_px.cuh
+      const u32 px_max = env_u32("VI_B200_EX_PX", VI_NUM_SMS, 0, 1u << 20);
+      if (vec_ok && b.nbig * nblk <= px_max)
+      {
+        // > 48 KB of dynamic shared memory: opt in (per device; a handful of launches per build)
+        VI_CUDA_TRY(cudaFuncSetAttribute(k_stats_big_exact_px<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(PxShared<16>)));
+        auto px_trace = [&](const char* what) -> int
+        {
+          if (!getenv("VI_B200_TRACE")) return VI_OK;
+          unsigned long long h[8][4];
+          VI_CUDA_TRY(cudaStreamSynchronize(st));
+          VI_CUDA_TRY(cudaMemcpyFromSymbol(h, g_px_dbg, sizeof(h)));
+          static const char* role[8] = {"chain", "verify0", "verify1", "variance", "-", "loader0", "loader1", "-"};
+          for (int w = 0; w < 8; ++w)
+            if (h[w][2])
+              fprintf(stderr, "[vi_b200] px %s level %d %-8s waitA %5.1f%% waitB %5.1f%% other %5.1f%% of %.2f Mcycles\n", what,
+                      level, role[w], 100.0 * h[w][0] / h[w][2], 100.0 * h[w][1] / h[w][2], 100.0 * h[w][3] / h[w][2],
+                      h[w][2] * 1e-6);
+          unsigned long long z[8][4] = {};
+          VI_CUDA_TRY(cudaMemcpyToSymbol(g_px_dbg, z, sizeof(z)));
+          return VI_OK;
+        };
+        k_stats_big_exact_px<16><<<b.nbig * nblk, PX_THREADS, sizeof(PxShared<16>), st>>>(
+            sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, dims, ctx->gstats);
+        px_trace("full");
+      }
+      else
+      {
+        const bool vec = vec_ok && env_u32("VI_B200_EX_VEC", 1, 0, 1) != 0;
+        const u32 ng = env_u32("VI_B200_EX_NG", EXNG_DEFAULT, 4, 12);
+#define CALL_BIGEX(VEC, NG)                                                                                   \
+  k_stats_big_exact<VEC, NG><<<b.nbig * nblk, 32, 0, st>>>(sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, \
+                                                           dims, ctx->gstats)
+        if (vec) { if (ng <= 4) CALL_BIGEX(true, 4); else if (ng <= 6) CALL_BIGEX(true, 6); else CALL_BIGEX(true, 10); }
+        else { if (ng <= 4) CALL_BIGEX(false, 4); else if (ng <= 6) CALL_BIGEX(false, 6); else CALL_BIGEX(false, 10); }
+#undef CALL_BIGEX
+      }
+      {
+        const u32 per = std::min(128u, std::max(1u, 2048u / b.nbig));
+        VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)b.nbig * 16, st));
+        k_idsum_big<<<b.nbig * per, 256, 0, st>>>(sg, ctx->big_list[cur], per, ctx->pid[cur], ctx->gacc);
+      }
+      k_finalize_big_exact<<<(b.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], b.nbig, ctx->gstats,
+                                                                      ctx->gacc, dims, mx, sout);
+      env.launches += 3;
+    }
+    if (b.minseg < t_big)
+    {
+      const u32 grid = (u32)(((u64)b.R * 32 + 255) / 256);
+#define CALL_EX(CHX) \
+  k_stats_small_exact<CHX><<<grid, 256, 0, st>>>(sg, b.R, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, mx, sout)
+      switch (env.chx)
+      {
+        case 1: CALL_EX(1); break;
+        case 2: CALL_EX(2); break;
+        case 3: CALL_EX(3); break;
+        case 4: CALL_EX(4); break;
+        default: CALL_EX(8); break;
+      }
+#undef CALL_EX
+      ++env.launches;
+    }
+  }
+  ev.e1 = env_event(ctx, env);
+
+  // ---- stable partition: three launches ------------------------------------------------------------------------
+  const FlagScan fs{ctx->fbits, ctx->wloc, ctx->ftile};
+  const int sibling = (mode == VI_MODE_FAST && env.sibling) ? 1 : 0;
+  k_flags<<<b.A / FL_TILE + 1, 256, 0, st>>>(lvp, &lvp->ticket[0], sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], rows, ld,
+                                            ctx->fbits, ctx->wloc, ctx->ftile);
+  k_children<<<(b.R + CH_TILE - 1) / CH_TILE, 256, 0, st>>>(lvp, &lvp->ticket[1], lvp + 1, ctx->h_lv + level + 1, sg, fs,
+                                                           ctx->seg_nlo, ctx->seg_hbase, ctx->c_pre, ctx->ctile,
+                                                           ctx->ctile_mm, env.t_sub, t_big, sibling, (u32)ctx->t_cap,
+                                                           ctx->chunk_first[nxt]);
+  NextLevel nx{ctx->seg[nxt], ctx->perm[nxt], ctx->pid[nxt], ctx->seg_of[nxt], ctx->big_list[nxt], ctx->bl_parent[nxt],
+               ctx->bl_sib[nxt], ctx->chunk_first[nxt]};
+  SubList sl{ctx->sub_start, ctx->sub_count, ctx->sub_rid, ctx->sub_row, ctx->sub_depth};
+  k_scatter<<<(b.A + 255) / 256, 256, 0, st>>>(lvp, lvp + 1, sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], fs,
+                                               ctx->seg_nlo, ctx->seg_hbase, ctx->c_pre, ctx->ctile, env.t_sub, t_big, sibling,
+                                               (u32)level + 1u, nx, tout, ctx->t_src, sl, ctx->sub_perm, ctx->sub_pid);
+  env.launches += 3;
+  ev.e2 = env_event(ctx, env);
+  return VI_OK;
+}
+
+// The level loop: processes seg[s.cur] (ranges of depth s.level) until no range with >= 2 points is left.
+// `rows` is the row store perm[] indexes.  `s` is the exact state of the first level; on return it holds the
+// final row / sub-tree cursors.
+static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* rows)
+{
+  cudaStream_t st = ctx->stream;
+  const int mode = env.mode;
+  const u32 t_big = env.t_big;
+  int rc = upload_level(ctx, s);
+  if (rc != VI_OK) return rc;
   // fast mode: the level's big-list slots and, per slot, whether its sums are derived (sibling derivation)
   u64 *gacc_cur = ctx->gacc, *gacc_prev = ctx->gacc_prev;
-  bool first_level = true;
-  if (mode == VI_MODE_FAST)
+  if (mode == VI_MODE_FAST && s.R > 0)
   {
     VI_CUDA_TRY(cudaMemsetAsync(ctx->seg[s.cur].bslot, 0xff, (size_t)s.R * sizeof(u32), st));
     if (s.nbig)
       k_init_bslot<<<(s.nbig + 255) / 256, 256, 0, st>>>(ctx->seg[s.cur].bslot, s.R, ctx->big_list[s.cur], s.nbig,
                                                          ctx->bl_parent[s.cur], ctx->bl_sib[s.cur]);
   }
-  while (s.R > 0)
+  const int first = s.level;
+  std::vector<LevelEvents> evs;  // per enqueued level, index level - first
+  LevelState known = s;          // exact state of level `known.level`
+  int level = s.level;           // next level to enqueue
+  int cur = s.cur;
+  const int lag = (int)env.lag;
+
+  // waits for the end of level known.level and reads the record of the next level the device wrote
+  auto absorb = [&]() -> int
   {
-    if (s.level >= VI_MAX_DEPTH)
+    const LevelEvents& ev = evs[known.level - first];
+    VI_CUDA_TRY(cudaEventSynchronize(ev.e2));
+    const LevelDev d = ctx->h_lv[known.level + 1];
+    if (d.err)
+      return ctx->fail(VI_ERR_CAPACITY, "range table capacity exceeded (degenerate input: too many one-child ranges)");
+    if (known.R > 0)
+    {
+      vi_level_info li{};
+      li.level = known.level;
+      li.ranges = known.R;
+      li.points = known.A;
+      li.rows_emitted = d.rows;
+      li.derived_points = (int32_t)known.derived;
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev.e0, ev.e1);
+      li.stats_ms = ms;
+      cudaEventElapsedTime(&ms, ev.e1, ev.e2);
+      li.partition_ms = ms;
+      ctx->levels.push_back(li);
+      ctx->info.point_visits += known.A;
+    }
+    known.A = d.A;
+    known.R = d.R;
+    known.nbig = d.nbig;
+    known.chunks = d.chunks;
+    known.minseg = d.minseg;
+    known.maxseg = d.maxseg;
+    known.derived = d.derived;
+    known.row_next = d.row_next;
+    known.sub_cnt = d.sub_cnt;
+    known.sub_pos = d.sub_pos;
+    ++known.level;
+    return VI_OK;
+  };
+
+  for (;;)
+  {
+    while (known.level + (lag - 1) < level)
+      if ((rc = absorb()) != VI_OK) return rc;
+    if (known.R == 0) break;  // nothing open at known.level: every level already enqueued behind it is a no-op
+    if (level >= VI_MAX_DEPTH)
+    {
+      // splitting a depth-62 range overflows rangeId: make sure such a range really exists before failing
+      while (known.level < level)
+        if ((rc = absorb()) != VI_OK) return rc;
+      if (known.R == 0) break;
       return ctx->fail(VI_ERR_OVERFLOW, "rangeId overflow: a range at depth 62 still holds more than one point "
                                         "(IndexBuilder.cs:99 checked(rangeId * 2 + 1))");
-    const int cur = s.cur, nxt = cur ^ 1;
-    const int mx = (s.level & 1) == 0;  // root max = true, children !max (IndexBuilder.cs:33,128-129)
-    SegLevel& sg = ctx->seg[cur];
-    const u32 A = s.A, R = s.R;
-    cudaEvent_t e0 = env_event(ctx, env);
-
-    // ---- statistics + split choice -----------------------------------------------------------------------
-    if (mode == VI_MODE_FAST)
-    {
-      if (s.nbig)
-      {
-        VI_CUDA_TRY(cudaMemsetAsync(gacc_cur, 0, (size_t)s.nbig * env.gstride * sizeof(u64), st));
-        launch_big_fast(ctx, env, rows, cur, s.nbig, s.chunks, mx, 1, gacc_cur, env.sibling ? 2 * t_big : 0xffffffffu,
-                        env.sibling ? ctx->bl_sib[cur] : nullptr);
-        // sibling derivation: the larger child of a big pair = parent - smaller child (k_emit_children chose them)
-        const bool may_derive = env.sibling && !first_level;
-        if (may_derive)
-        {
-          k_derive_big<<<s.nbig, 256, 0, st>>>(gacc_cur, gacc_prev, ctx->bl_parent[cur], ctx->bl_sib[cur], s.nbig,
-                                               (u32)env.gstride);
-          ++env.launches;
-        }
-        // ranges that fit one chunk and one column pass were finished by their CTA
-        const int single_pass = (ld / 4) <= env.shp_big.ts * env.shp_big.ch;
-        if (!single_pass || s.maxseg > VI_CHUNK || may_derive)
-        {
-          k_finalize_big_fast<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, gacc_cur, ld,
-                                                                         dims, env.qinv, mx, sout, rows, ctx->perm[cur],
-                                                                         single_pass, 0, nullptr, ctx->bl_parent[cur]);
-          ++env.launches;
-        }
-        std::swap(gacc_cur, gacc_prev);
-      }
-      first_level = false;
-      // warp-per-range class (teams of a warp share one range); for TS == 32 it also covers the team class
-      const u32 wlo = shp.ts == 32 ? 2u : t_team;
-      if (s.minseg < t_big && s.maxseg >= wlo)
-      {
-#define CALL_WARP(TS, CH, FULL)                                                                              \
-  k_stats_small_fast<TS, CH, FULL, true><<<(u32)(((u64)R * 32 + 255) / 256), 256, 0, st>>>(                   \
-      sg, R, wlo, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout)
-        FAST_DISPATCH(shp, CALL_WARP);
-#undef CALL_WARP
-        ++env.launches;
-      }
-      if (shp.ts < 32 && s.minseg < t_team)
-      {
-#define CALL_TEAM(TS, CH, FULL)                                                                              \
-  k_stats_small_fast<TS, CH, FULL, false><<<(u32)(((u64)R * TS + 255) / 256), 256, 0, st>>>(                  \
-      sg, R, 2u, t_team, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout)
-        FAST_DISPATCH(shp, CALL_TEAM);
-#undef CALL_TEAM
-        ++env.launches;
-      }
     }
-    else
+    // bounds on this level's sizes from the last record the host knows (`d` levels above)
+    const int d = level - known.level;
+    LevelState b = known;
+    if (d > 0)
     {
-      if (s.nbig)
-      {
-        const u32 nblk = (u32)((dims + 31) / 32);
-        const bool vec_ok = ld % 4 == 0 && ((uintptr_t)rows & 15) == 0;
-        // top levels (few chains in the whole GPU): the warp-specialised pipeline, vi_stats_exact_px.cuh
-        const u32 px_max = env_u32("VI_B200_EX_PX", VI_NUM_SMS, 0, 1u << 20);
-        if (vec_ok && s.nbig * nblk <= px_max)
-        {
-          // > 48 KB of dynamic shared memory: opt in (per device; a handful of launches per build)
-          VI_CUDA_TRY(cudaFuncSetAttribute(k_stats_big_exact_px<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)sizeof(PxShared<16>)));
-          auto px_trace = [&](const char* what) -> int
-          {
-            if (!getenv("VI_B200_TRACE")) return VI_OK;
-            unsigned long long h[8][4];
-            VI_CUDA_TRY(cudaStreamSynchronize(st));
-            VI_CUDA_TRY(cudaMemcpyFromSymbol(h, g_px_dbg, sizeof(h)));
-            static const char* role[8] = {"chain", "verify0", "verify1", "variance", "-", "loader0", "loader1", "-"};
-            for (int w = 0; w < 8; ++w)
-              if (h[w][2])
-                fprintf(stderr, "[vi_b200] px %s level %d %-8s waitA %5.1f%% waitB %5.1f%% other %5.1f%% of %.2f Mcycles\n", what,
-                        s.level, role[w], 100.0 * h[w][0] / h[w][2], 100.0 * h[w][1] / h[w][2], 100.0 * h[w][3] / h[w][2],
-                        h[w][2] * 1e-6);
-            unsigned long long z[8][4] = {};
-            VI_CUDA_TRY(cudaMemcpyToSymbol(g_px_dbg, z, sizeof(z)));
-            return VI_OK;
-          };
-          k_stats_big_exact_px<16><<<s.nbig * nblk, PX_THREADS, sizeof(PxShared<16>), st>>>(
-              sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, dims, ctx->gstats);
-          px_trace("full");
-        }
-        else
-        {
-        const bool vec = ld % 4 == 0 && ((uintptr_t)rows & 15) == 0 && env_u32("VI_B200_EX_VEC", 1, 0, 1) != 0;
-        const u32 ng = env_u32("VI_B200_EX_NG", EXNG_DEFAULT, 4, 12);
-#define CALL_BIGEX(VEC, NG)                                                                                   \
-  k_stats_big_exact<VEC, NG><<<s.nbig * nblk, 32, 0, st>>>(sg, ctx->big_list[cur], nblk, ctx->perm[cur], rows, ld, \
-                                                           dims, ctx->gstats)
-        if (vec) { if (ng <= 4) CALL_BIGEX(true, 4); else if (ng <= 6) CALL_BIGEX(true, 6); else CALL_BIGEX(true, 10); }
-        else { if (ng <= 4) CALL_BIGEX(false, 4); else if (ng <= 6) CALL_BIGEX(false, 6); else CALL_BIGEX(false, 10); }
-#undef CALL_BIGEX
-        }
-        {
-          const u32 per = std::min(128u, std::max(1u, 2048u / s.nbig));
-          VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)s.nbig * 16, st));
-          k_idsum_big<<<s.nbig * per, 256, 0, st>>>(sg, ctx->big_list[cur], per, ctx->pid[cur], ctx->gacc);
-        }
-        k_finalize_big_exact<<<(s.nbig * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], s.nbig, ctx->gstats,
-                                                                        ctx->gacc, dims, mx, sout);
-        env.launches += 3;
-      }
-      if (s.minseg < t_big)
-      {
-        const u32 grid = (u32)(((u64)R * 32 + 255) / 256);
-#define CALL_EX(CHX) \
-  k_stats_small_exact<CHX><<<grid, 256, 0, st>>>(sg, R, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, mx, sout)
-        switch (env.chx)
-        {
-          case 1: CALL_EX(1); break;
-          case 2: CALL_EX(2); break;
-          case 3: CALL_EX(3); break;
-          case 4: CALL_EX(4); break;
-          default: CALL_EX(8); break;
-        }
-#undef CALL_EX
-        ++env.launches;
-      }
+      const u64 grow = 1ull << d;
+      b.R = (u32)std::min<u64>((u64)known.R * grow, (u64)known.A / 2);
+      b.nbig = (u32)std::min<u64>((u64)known.nbig * grow, (u64)known.A / t_big);
+      b.chunks = known.A / VI_CHUNK + b.nbig;
+      b.minseg = 2;
     }
-    cudaEvent_t e1 = env_event(ctx, env);
-
-    // ---- stable partition ----------------------------------------------------------------------------------
-    const u32 W = (A + 31) / 32;
-    k_flags<<<W / 8 + 1, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], rows, ld, A, ctx->fbits,
-                                       ctx->wpre);
-    ++env.launches;
-    scan_exclusive<u32>(ctx, ctx->wpre, W + 1, env.launches);
-    k_seg_children<<<(R + 255) / 256, 256, 0, st>>>(sg, R, ctx->wpre, ctx->fbits, ctx->seg_nlo, ctx->seg_hbase,
-                                                    ctx->c_rows, ctx->c_actpos, ctx->c_sub, env.t_sub);
-    ++env.launches;
-    scan_exclusive<u32>(ctx, ctx->c_rows, R, env.launches);
-    scan_exclusive<u64>(ctx, ctx->c_actpos, R, env.launches);
-    if (env.t_sub) scan_exclusive<u64>(ctx, ctx->c_sub, R, env.launches);
-    else VI_CUDA_TRY(cudaMemsetAsync(ctx->c_sub, 0, ((size_t)R + 1) * 8, st));
-    {
-      const u32 init[8] = {0u, 0u, 0u, 0u, 0xffffffffu, 0u, 0u, 0u};  // [0] nbig [1] err [4] minseg [5] maxseg
-      VI_CUDA_TRY(cudaMemcpyAsync(lvl_counters, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    }
-    const u32 row_base_next = s.row_next;
-    k_emit_children<<<(R + 255) / 256, 256, 0, st>>>(sg, R, ctx->seg_nlo, ctx->c_rows, ctx->c_actpos, ctx->seg[nxt],
-                                                     row_base_next, (u32)ctx->t_cap, tout, ctx->big_list[nxt], t_big,
-                                                     lvl_counters, ctx->c_sub, env.t_sub, s.sub_cnt, s.sub_pos,
-                                                     (u32)s.level + 1u, ctx->sub_start, ctx->sub_count, ctx->sub_rid,
-                                                     ctx->sub_row, ctx->sub_depth, ctx->bl_parent[nxt], ctx->bl_sib[nxt],
-                                                     (mode == VI_MODE_FAST && env.sibling) ? 1 : 0);
-    k_scatter<<<(A + 255) / 256, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], A, ctx->fbits,
-                                               ctx->wpre, ctx->seg_nlo, ctx->seg_hbase, ctx->c_rows, ctx->c_actpos,
-                                               row_base_next, ctx->perm[nxt], ctx->pid[nxt], ctx->seg_of[nxt], ctx->t_id,
-                                               ctx->t_src, lvl_counters, ctx->c_sub, env.t_sub, s.sub_pos, ctx->sub_perm,
-                                               ctx->sub_pid);
-    env.launches += 2;
-    const u32 big_bound = A / t_big + 1;
-    u32* chunk_arr = nullptr;
-    if (mode == VI_MODE_FAST)
-    {
-      chunk_arr = ctx->chunk_first;
-      k_big_chunks<<<(big_bound + 255) / 256, 256, 0, st>>>(ctx->seg[nxt].count, ctx->big_list[nxt], lvl_counters,
-                                                            chunk_arr, big_bound, ctx->bl_parent[nxt]);
-      ++env.launches;
-      scan_exclusive<u32>(ctx, chunk_arr, big_bound, env.launches);
-    }
-    k_totals<<<1, 1, 0, st>>>(ctx->c_rows, ctx->c_actpos, ctx->c_sub, R, lvl_counters, chunk_arr, big_bound, ctx->totals);
-    ++env.launches;
-    cudaEvent_t e2 = env_event(ctx, env);
-    VI_CUDA_TRY(cudaStreamSynchronize(st));
-    const LevelTotals tt = *ctx->totals;
-    if (tt.err)
-      return ctx->fail(VI_ERR_CAPACITY, "range table capacity exceeded (degenerate input: too many one-child ranges)");
-    vi_level_info li{};
-    li.level = s.level;
-    li.ranges = R;
-    li.points = A;
-    li.rows_emitted = tt.rows;
-    li.derived_points = (int32_t)s.derived;
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    li.stats_ms = ms;
-    cudaEventElapsedTime(&ms, e1, e2);
-    li.partition_ms = ms;
-    ctx->levels.push_back(li);
-    ctx->info.point_visits += A;
-
-    s.row_next = row_base_next + tt.rows;
-    s.R = tt.segs;
-    s.A = tt.pos;
-    s.nbig = tt.nbig;
-    s.chunks = tt.chunks;
-    s.minseg = tt.minseg;
-    s.maxseg = tt.maxseg;
-    s.derived = tt.derived;
-    s.sub_cnt += tt.subs;
-    s.sub_pos += tt.subpos;
-    s.cur = nxt;
-    ++s.level;
+    LevelEvents ev;
+    rc = enqueue_level(ctx, env, b, level, cur, d == 0, level == first, rows, gacc_cur, gacc_prev, ev);
+    if (rc != VI_OK) return rc;
+    evs.push_back(ev);
+    std::swap(gacc_cur, gacc_prev);
+    cur ^= 1;
+    ++level;
   }
+  while (known.level < level)
+    if ((rc = absorb()) != VI_OK) return rc;
+  s.A = 0;
+  s.R = 0;
+  s.row_next = known.row_next;
+  s.sub_cnt = known.sub_cnt;
+  s.sub_pos = known.sub_pos;
+  s.level = known.level;
+  s.cur = cur;
   return run_subtrees(ctx, env, s, rows);
 }
 
-static int finish_table(vi_ctx* ctx, BuildEnv& env, u32 total_rows, cudaEvent_t ev_begin)
+static int finish_table(vi_ctx* ctx, BuildEnv& env, u32 total_rows, cudaEvent_t ev_begin, const float* src_rows)
 {
+  ctx->src_rows = src_rows;  // the store the table's t_src indexes (candidate verification, top-k)
   cudaStream_t st = ctx->stream;
   if (total_rows > 0)
   {
@@ -826,7 +903,7 @@ static int build_single(vi_ctx* ctx, BuildEnv& env)
     vi_level_info li{};
     li.rows_emitted = 1;
     ctx->levels.push_back(li);
-    return finish_table(ctx, env, 1, ev_begin);
+    return finish_table(ctx, env, 1, ev_begin, ctx->rows);
   }
   int rc = alloc_workspace(ctx, ctx->n);
   if (rc != VI_OK) return rc;
@@ -852,11 +929,11 @@ static int build_single(vi_ctx* ctx, BuildEnv& env)
   if (s.nbig)
   {
     const u32 h[2] = {0u, s.chunks};
-    VI_CUDA_TRY(cudaMemcpyAsync(ctx->chunk_first, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    VI_CUDA_TRY(cudaMemcpyAsync(ctx->chunk_first[0], h, sizeof(h), cudaMemcpyHostToDevice, st));
   }
   rc = run_levels(ctx, env, s, ctx->rows);
   if (rc != VI_OK) return rc;
-  return finish_table(ctx, env, s.row_next, ev_begin);
+  return finish_table(ctx, env, s.row_next, ev_begin, ctx->rows);
 }
 
 // =============================================================================================================
@@ -924,7 +1001,7 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
   memcpy(&amax, &amax_bits, 4);
   set_q_exponent(ctx, env, amax);
   if (nglobal >= 0x7fffffffull) return ctx->fail(VI_ERR_CAPACITY, "more than 2^31-2 points");
-  if (nglobal == 0) return finish_table(ctx, env, 0, ev_begin);
+  if (nglobal == 0) return finish_table(ctx, env, 0, ev_begin, nullptr);
 
   // ---- phase A: shared levels -------------------------------------------------------------------------------
   int L = 1;
@@ -942,8 +1019,12 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
                                                       ctx->seg[0], ctx->big_list[0], ctx->t_rid, ctx->t_low, ctx->t_high);
     ++env.launches;
   }
-  u64* leaf_ids = ctx->c_actpos;  // scratch (unused by the shared phase): ids of shared leaf rows, owner writes
+  // scratch (the level loop's per-range prefix array is unused until phase C): ids of shared leaf rows (the holder
+  // writes), then the small host-built tables of this phase
+  u64* leaf_ids = reinterpret_cast<u64*>(ctx->c_pre);
+  u32* scratch32 = reinterpret_cast<u32*>(ctx->c_pre) + 16384;
   VI_CUDA_TRY(cudaMemsetAsync(leaf_ids, 0, 4096 * sizeof(u64), st));
+  VI_CUDA_TRY(cudaMemsetAsync(ctx->lv, 0, sizeof(LevelDev) * VI_LV_N, st));
   if (nglobal == 1)
   {
     if (nloc == 1)
@@ -952,6 +1033,7 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
   }
   StatsOut sout{ctx->t_dim, ctx->t_mid, ctx->t_id};
   u32* lvl_counters = ctx->counters + 16;
+  const FlagScan fs{ctx->fbits, ctx->wloc, ctx->ftile};
 
   for (; level < L && !segs.empty(); ++level)
   {
@@ -978,33 +1060,37 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
       A += segs[i].lcount;
     }
     h_cf[R] = chunks;
+    LevelDev hl{};
+    hl.A = A;
+    hl.R = R;
+    hl.nbig = R;
+    hl.chunks = chunks;
+    std::vector<LevelDev> h_lvrec{hl};
+    LevelDev* lvp = ctx->lv + level;
     if ((rc = upload(ctx, sg.start, h_start)) || (rc = upload(ctx, sg.count, h_count)) || (rc = upload(ctx, sg.row, h_row)) ||
         (rc = upload(ctx, sg.rid, h_srid)) || (rc = upload(ctx, ctx->big_list[cur], h_big)) ||
-        (rc = upload(ctx, ctx->chunk_first, h_cf)))
+        (rc = upload(ctx, ctx->chunk_first[cur], h_cf)) || (rc = upload(ctx, lvp, h_lvrec)))
       return rc;
     // local sums of every range -> gacc, one all-reduce, identical split on every rank
     VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)R * env.gstride * sizeof(u64), st));
-    if (chunks > 0) launch_big_fast(ctx, env, ctx->rows, cur, R, chunks, mx, 0, ctx->gacc, 0xffffffffu, nullptr);
+    if (chunks > 0) launch_big_fast(ctx, env, lvp, ctx->rows, cur, chunks, mx, 0, ctx->gacc, 0xffffffffu, nullptr);
     VI_CUDA_TRY(cudaStreamSynchronize(st));
     if (ctx->allreduce(ctx->coll_user, ctx->gacc, (int64_t)((size_t)R * env.gstride)) != 0)
       return ctx->fail(VI_ERR_CUDA, "all-reduce callback failed");
     VI_CUDA_TRY(cudaMemsetAsync(lvl_counters, 0, 32, st));
-    k_finalize_big_fast<<<(R * 32 + 255) / 256, 256, 0, st>>>(sg, ctx->big_list[cur], R, ctx->gacc, ld, dims, env.qinv,
-                                                              mx, sout, ctx->rows, ctx->perm[cur], 0, 1, lvl_counters + 1, nullptr);
+    k_finalize_big_fast<<<(R * 32 + 255) / 256, 256, 0, st>>>(lvp, sg, ctx->big_list[cur], ctx->gacc, nullptr, ld, dims,
+                                                              env.qinv, mx, sout, ctx->rows, ctx->perm[cur], 0, 1,
+                                                              lvl_counters + 1, nullptr, nullptr);
     ++env.launches;
     cudaEvent_t e1 = env_event(ctx, env);
     // local partition flags and child sizes
     std::vector<u32> h_nlo(R, 0);
     if (A > 0)
     {
-      const u32 W = (A + 31) / 32;
-      k_flags<<<W / 8 + 1, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], ctx->rows, ld, A, ctx->fbits,
-                                         ctx->wpre);
-      ++env.launches;
-      scan_exclusive<u32>(ctx, ctx->wpre, W + 1, env.launches);
-      k_seg_children<<<(R + 255) / 256, 256, 0, st>>>(sg, R, ctx->wpre, ctx->fbits, ctx->seg_nlo, ctx->seg_hbase,
-                                                      ctx->c_rows, ctx->c_actpos + 4096, ctx->c_sub, 0u);
-      ++env.launches;
+      k_flags<<<A / FL_TILE + 1, 256, 0, st>>>(lvp, &lvp->ticket[0], sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur],
+                                               ctx->rows, ld, ctx->fbits, ctx->wloc, ctx->ftile);
+      k_seg_nlo<<<(R + 255) / 256, 256, 0, st>>>(sg, R, fs, ctx->seg_nlo, ctx->seg_hbase);
+      env.launches += 2;
       VI_CUDA_TRY(cudaMemcpyAsync(h_nlo.data(), ctx->seg_nlo, R * 4, cudaMemcpyDeviceToHost, st));
     }
     u32 errflag = 0;
@@ -1055,14 +1141,14 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
     if (T >= 4096) return ctx->fail(VI_ERR_CAPACITY, "too many shared rows");
     if (A > 0)
     {
-      u32* d = ctx->c_rows;  // scratch for the six per-range arrays
+      u32* d = scratch32;  // the six per-range arrays
       if ((rc = upload(ctx, d, lo_dst)) || (rc = upload(ctx, d + R, hi_dst)) || (rc = upload(ctx, d + 2 * R, lo_seg)) ||
           (rc = upload(ctx, d + 3 * R, hi_seg)) || (rc = upload(ctx, (int*)(d + 4 * R), lo_leaf)) ||
           (rc = upload(ctx, (int*)(d + 5 * R), hi_leaf)))
         return rc;
       ShScatter sc{d, d + R, d + 2 * R, d + 3 * R, (const int*)(d + 4 * R), (const int*)(d + 5 * R)};
-      k_scatter_shared<<<(A + 255) / 256, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], A, ctx->fbits,
-                                                        ctx->wpre, ctx->seg_hbase, sc, ctx->perm[nxt], ctx->pid[nxt],
+      k_scatter_shared<<<(A + 255) / 256, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], A, fs,
+                                                        ctx->seg_hbase, sc, ctx->perm[nxt], ctx->pid[nxt],
                                                         ctx->seg_of[nxt], leaf_ids, ctx->t_src);
       ++env.launches;
     }
@@ -1189,11 +1275,11 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
       std::vector<u32> h_start(RL), h_count(RL);
       for (u32 i = 0; i < RL; ++i) { h_start[i] = segs[i].start; h_count[i] = segs[i].lcount; }
       if ((rc = upload(ctx, ctx->seg[cur].start, h_start)) || (rc = upload(ctx, ctx->seg[cur].count, h_count)) ||
-          (rc = upload(ctx, ctx->c_rows, send_base)))
+          (rc = upload(ctx, scratch32, send_base)))
         return rc;
       const size_t threads = (size_t)A * (ld / 4);
       k_pack_rows<<<(u32)((threads + 255) / 256), 256, 0, st>>>(ctx->seg[cur], ctx->seg_of[cur], ctx->perm[cur],
-                                                                ctx->pid[cur], ctx->rows, ld, A, ctx->c_rows, send_rows,
+                                                                ctx->pid[cur], ctx->rows, ld, A, scratch32, send_rows,
                                                                 send_ids);
       ++env.launches;
     }
@@ -1258,11 +1344,11 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
     if (s.R > 0)
     {
       SegLevel& f = ctx->seg[0];
-      u32* d = ctx->c_rows;
+      u32* d = scratch32;
       const u32 np = (u32)piece_dst.size();
       if ((rc = upload(ctx, f.start, f_start)) || (rc = upload(ctx, f.count, f_count)) || (rc = upload(ctx, f.rid, f_rid)) ||
           (rc = upload(ctx, f.row, f_row)) || (rc = upload(ctx, ctx->big_list[0], f_big)) ||
-          (rc = upload(ctx, ctx->chunk_first, f_cf)) || (rc = upload(ctx, d, piece_dst)) ||
+          (rc = upload(ctx, ctx->chunk_first[0], f_cf)) || (rc = upload(ctx, d, piece_dst)) ||
           (rc = upload(ctx, d + np, piece_src)) || (rc = upload(ctx, d + 2 * np, piece_seg)))
         return rc;
       k_forest_init<<<(s.A + 255) / 256, 256, 0, st>>>(s.A, np, d, d + np, d + 2 * np, ctx->own_ids, ctx->perm[0],
@@ -1272,7 +1358,7 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
       if (rc != VI_OK) return rc;
     }
   }
-  return finish_table(ctx, env, s.row_next, ev_begin);
+  return finish_table(ctx, env, s.row_next, ev_begin, ctx->own_n > 0 ? ctx->own_rows : ctx->rows);
 }
 
 // Replicates the table of a multi-rank build on every rank (for query-sharded search).

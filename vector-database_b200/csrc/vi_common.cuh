@@ -42,20 +42,42 @@ struct SegLevel
   u32* bslot = nullptr;   // fast mode: index of the range in the level's big list (its gacc slot), or 0xffffffff
 };
 
-struct LevelTotals  // pinned host, written by the device at the end of every level
+// State of one tree level, resident on the device: every kernel of a level reads its sizes from here and the last
+// kernel of the partition pass writes the next level's record (and a copy into pinned host memory), so the level
+// loop never has to wait for the host to learn a size before it can launch (vi_build.cu run_levels).
+struct LevelDev
 {
-  u32 rows;      // table rows created for the next level (non-empty children)
-  u32 segs;      // next-level segments (children with >= 2 points)
-  u32 pos;       // next-level active positions
-  u32 nbig;      // next-level big segments
-  u32 chunks;    // next-level fast-mode chunk count
-  u32 err;       // range table capacity exceeded
-  u32 minseg;    // smallest / largest next-level range
+  u32 A;          // active positions (points in open ranges)
+  u32 R;          // open ranges (segments, each >= 2 points)
+  u32 nbig;       // of them, big ones (fast mode: chunked statistics; exact mode: one chain per (range, dim))
+  u32 chunks;     // fast mode: chunk CTAs of the statistics kernel
+  u32 minseg;     // smallest / largest open range
   u32 maxseg;
-  u32 subs;      // children handed to the sub-tree kernel this level, and their points
-  u32 subpos;
-  u32 derived;   // next-level points in ranges whose sums are derived (parent - sibling), fast mode
+  u32 derived;    // fast mode: points in big ranges whose sums are derived as parent - sibling
+  u32 row_next;   // first free table row
+  u32 sub_cnt;    // sub-tree list so far: entries and points
+  u32 sub_pos;
+  u32 err;        // 1 = range table capacity exceeded
+  u32 rows;       // table rows created by the partition pass that produced this level (accounting)
+  u32 ticket[2];  // last-block tickets of the level's two scans (k_flags, k_children)
+  u32 pad[2];
 };
+static_assert(sizeof(LevelDev) == 64, "LevelDev is copied as 4 x uint4");
+constexpr int VI_LV_N = VI_MAX_DEPTH + 4;
+
+// One tile aggregate / prefix of k_children's scan over the level's ranges (vi_partition.cuh)
+struct ChildAgg
+{
+  u32 rows;     // table rows of the children (non-empty ones)
+  u32 act_cnt;  // children that stay ranges of the next level
+  u32 act_pos;  // their points
+  u32 sub_cnt;  // children handed to the sub-tree kernel
+  u32 sub_pos;  // their points
+  u32 big_cnt;  // big children (next level's big list slots)
+  u32 chunks;   // chunk CTAs of the big children that are summed
+  u32 derived;  // points of the big children that are derived
+};
+static_assert(sizeof(ChildAgg) == 32, "ChildAgg is moved as 2 x uint4");
 
 struct vi_ctx
 {
@@ -78,14 +100,17 @@ struct vi_ctx
   u32* seg_of[2] = {nullptr, nullptr};
   SegLevel seg[2];
   u32* big_list[2] = {nullptr, nullptr};    // segment indexes of big segments
-  u32* chunk_first = nullptr;               // exclusive scan of chunks per big slot (+ total)
+  u32* chunk_first[2] = {nullptr, nullptr}; // exclusive scan of chunks per big slot (+ total), per level parity
   u32* fbits = nullptr;                     // hi flags, 1 bit per position
-  u32* wpre = nullptr;                      // exclusive popcount prefix per flag word (+ total)
+  u32* wloc = nullptr;                      // hi flags before each flag word inside its 2048-position tile
+  u32* ftile = nullptr;                     // per flag tile: hi count, then (last block) exclusive prefix (+ total)
   u32* seg_nlo = nullptr;                   // per segment: low child size
   u32* seg_hbase = nullptr;                 // per segment: hi flags before its first position
-  u32* c_rows = nullptr;                    // per segment child row count (scanned in place, + total)
-  u64* c_actpos = nullptr;                  // per segment (active children << 32 | active positions) (+ total)
-  u64* c_sub = nullptr;                     // per segment (sub-tree children << 32 | their points) (+ total)
+  ChildAgg* c_pre = nullptr;                // per segment: exclusive prefix of its children's counts inside its tile
+  ChildAgg* ctile = nullptr;                // per 1024-segment tile: aggregate, then exclusive prefix
+  uint2* ctile_mm = nullptr;                // per tile: (min, max) size of the children that stay ranges
+  LevelDev* lv = nullptr;                   // device level records [VI_LV_N]
+  LevelDev* h_lv = nullptr;                 // pinned host copies, written by the device
   u32* sub_perm = nullptr;                  // sub-tree position space: row index / id per point
   i64* sub_pid = nullptr;
   u32* sub_start = nullptr;                 // sub-tree list
@@ -94,14 +119,13 @@ struct vi_ctx
   u32* sub_row = nullptr;
   u32* sub_depth = nullptr;
   u64* sub_stats = nullptr;                 // [64] points + [64] ranges per depth, then the kernel's 2 counters
-  void* scan_tmp = nullptr;                 // block sums for scans
+  void* scan_tmp = nullptr;                 // block sums for scans (multi-rank shared phase)
   u64* gacc_prev = nullptr;                 // fast mode: the previous level's gacc (sibling derivation)
   u32* bl_parent[2] = {nullptr, nullptr};   // per big-list slot: the parent's slot in gacc_prev if the range's sums are
   u32* bl_sib[2] = {nullptr, nullptr};      //   derived as parent - sibling (bl_sib = the sibling's slot), else 0xffffffff
   u64* gacc = nullptr;                      // fast mode: per big slot [dims][4] + [2] id sums
   float2* gstats = nullptr;                 // exact mode: per big slot [dims] (mean, q)
   u32* counters = nullptr;                  // device counters (nbig_next, ...)
-  LevelTotals* totals = nullptr;            // pinned host
   float* d_absmax = nullptr;
 
   // table
@@ -116,6 +140,8 @@ struct vi_ctx
   int4* t_node = nullptr;  // packed traversal rows (dim, mid, low|id.lo, high|id.hi)
   int* t_src = nullptr;    // leaf rows: row index of the point in `rows` (for candidate verification)
   bool built = false;
+  const float* src_rows = nullptr;  // the row store the table's t_src indexes (rows, or own_rows after a multi-rank
+                                    // build); null when the table has no vectors behind it (imported / replicated)
 
   vi_build_info info{};
   std::vector<vi_level_info> levels;
@@ -193,11 +219,25 @@ __device__ __forceinline__ float ldg_f_gather(const float* p)
   return r;
 }
 
-// hi flags before position x: word prefix + bits below x in its word
-__device__ __forceinline__ u32 hi_before(const u32* __restrict__ wpre, const u32* __restrict__ fbits, u32 x)
+// ---- hi-flag prefix: tile prefix + word prefix inside the tile + bits below x in its word ------------------------
+constexpr int FL_ITEMS = 8;                    // positions per thread of k_flags
+constexpr int FL_TILE = 256 * FL_ITEMS;        // positions per CTA
+constexpr int FL_WORDS = FL_TILE / 32;         // flag words per tile
+constexpr int FL_WORDS_LOG2 = 6;
+static_assert((1 << FL_WORDS_LOG2) == FL_WORDS, "tile size");
+
+struct FlagScan
 {
-  u32 w = x >> 5, b = x & 31;
-  return wpre[w] + __popc(fbits[w] & ((1u << b) - 1u));
+  const u32* fbits;
+  const u32* wloc;
+  const u32* ftile;
+};
+
+// hi flags among positions [0, x); valid for x <= A (k_flags covers position A itself)
+__device__ __forceinline__ u32 hi_before(const FlagScan& f, u32 x)
+{
+  const u32 w = x >> 5, b = x & 31;
+  return f.ftile[w >> FL_WORDS_LOG2] + f.wloc[w] + __popc(f.fbits[w] & ((1u << b) - 1u));
 }
 
 // build entry points implemented in vi_build.cu / vi_search.cu

@@ -118,3 +118,49 @@ static void scan_exclusive(vi_ctx* ctx, T* data, u32 n, int64_t& launches)
   k_scan_add<T><<<nb, SCAN_THREADS, 0, ctx->stream>>>(data, bsum, n);
   launches += 3;
 }
+
+// ---- in-kernel scans of the partition pass (vi_partition.cuh) ------------------------------------------------------
+// Exclusive scan of a[0..m) in place by ONE CTA of NT threads, a[m] <- total.  Used by the last CTA of a kernel over
+// the per-tile aggregates the other CTAs published (threadfence + ticket): loads bypass L1.
+template <typename T, int NT>
+__device__ __forceinline__ void cta_scan_inplace(T* a, u32 m)
+{
+  constexpr int ITEMS = 4;
+  __shared__ T s_wsum[NT / 32];
+  __shared__ T s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (u32 base = 0; base < m; base += NT * ITEMS)
+  {
+    const u32 i0 = base + threadIdx.x * ITEMS;
+    T v[ITEMS];
+    T run = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k)
+    {
+      const T t = (i0 + k < m) ? __ldcg(a + i0 + k) : T(0);
+      v[k] = run;
+      run += t;
+    }
+    const T incl = warp_inclusive_scan(run);
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    T woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w)
+    {
+      const T y = s_wsum[w];
+      if (w < warp) woff += y;
+      total += y;
+    }
+    const T off = s_carry + woff + incl - run;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k)
+      if (i0 + k < m) a[i0 + k] = v[k] + off;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a[m] = s_carry;
+}

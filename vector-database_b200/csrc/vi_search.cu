@@ -262,7 +262,7 @@ int vi_verify_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float distan
   }
   if (total_in >= (int64_t)0xfffffff0) return ctx->fail(VI_ERR_CAPACITY, "too many candidates to verify in one call");
   u32* keep = ctx->verify_keep;
-  k_verify_flags<<<(u32)((total_in + 127) / 128), 128, 0, st>>>(ctx->own_rows ? ctx->own_rows : ctx->rows, ctx->ld, ctx->dims, d_queries, ctx->dims,
+  k_verify_flags<<<(u32)((total_in + 127) / 128), 128, 0, st>>>(ctx->src_rows, ctx->ld, ctx->dims, d_queries, ctx->dims,
                                                                 d_offsets_in, (u32)nq, ctx->search_src, total_in, distance,
                                                                 keep);
   k_scan_u32_single<<<1, 1024, 0, st>>>(keep, (u32)total_in);

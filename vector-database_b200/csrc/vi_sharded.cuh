@@ -22,17 +22,16 @@ struct ShScatter  // per range s of the current shared level (device arrays)
 
 __global__ void __launch_bounds__(256)
 k_scatter_shared(SegLevel sg, const u32* __restrict__ seg_of, const u32* __restrict__ perm, const i64* __restrict__ pid,
-                 u32 A, const u32* __restrict__ fbits, const u32* __restrict__ wpre, const u32* __restrict__ seg_hbase,
-                 ShScatter sc, u32* __restrict__ perm_n, i64* __restrict__ pid_n, u32* __restrict__ seg_of_n,
+                 u32 A, FlagScan fs, const u32* __restrict__ seg_hbase, ShScatter sc, u32* __restrict__ perm_n, i64* __restrict__ pid_n, u32* __restrict__ seg_of_n,
                  u64* __restrict__ leaf_ids, int* __restrict__ t_src)
 {
   const u32 p = blockIdx.x * 256u + threadIdx.x;
   if (p >= A) return;
   const u32 s = seg_of[p];
   const u32 S = sg.start[s];
-  const u32 w = fbits[p >> 5];
+  const u32 w = fs.fbits[p >> 5];
   const bool hi = (w >> (p & 31)) & 1u;
-  const u32 hb = wpre[p >> 5] + __popc(w & ((1u << (p & 31)) - 1u)) - seg_hbase[s];
+  const u32 hb = hi_before(fs, p) - seg_hbase[s];
   const u32 rank = hi ? hb : (p - S) - hb;
   const u32 dstb = hi ? sc.hi_dst[s] : sc.lo_dst[s];
   const u32 r = perm[p];

@@ -111,9 +111,11 @@ __device__ __forceinline__ float qfx_mid(i64 s1, u32 n, double qinv)
 
 template <int TS, int CH, bool FULL, bool WPS>
 __global__ void __launch_bounds__(256, (CH == 1) ? 4 : ((TS * CH <= 32) ? 3 : 1))
-k_stats_small_fast(SegLevel sg, u32 R, u32 nmin, u32 nmax, const u32* __restrict__ perm, const i64* __restrict__ pid,
-                   const float* __restrict__ rows, int ld, int dims, float qk, double qinv, int mx, StatsOut out)
+k_stats_small_fast(const LevelDev* __restrict__ lvp, SegLevel sg, u32 nmin, u32 nmax, const u32* __restrict__ perm,
+                   const i64* __restrict__ pid, const float* __restrict__ rows, int ld, int dims, float qk, double qinv, int mx,
+                   StatsOut out)
 {
+  const u32 R = lvp->R;
   constexpr int NTW = 32 / TS;            // teams per warp
   constexpr int TPS = WPS ? NTW : 1;      // teams sharing one range
   constexpr int GS = WPS ? 32 : TS;       // lanes sharing one range
@@ -289,11 +291,13 @@ constexpr int BIG_NST = 4;  // cp.async ring depth of the pipelined chunk kernel
 // UNR: register-prefetch unroll depth, or 0 for the cp.async ring (dynamic shared memory BIG_NST*CH*256*16 bytes)
 template <int TS, int CH, bool FULL, int UNR>
 __global__ void __launch_bounds__(256, (CH == 1) ? 4 : ((TS * CH <= 32) ? 3 : 1))
-k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __restrict__ chunk_first, u32 nbig,
-                 const u32* __restrict__ perm, const i64* __restrict__ pid, const float* __restrict__ rows, int ld,
-                 int dims, float qk, double qinv, int mx, StatsOut out, u64* __restrict__ gacc, int allow_whole,
-                 u32 keep_thr, const u32* __restrict__ bl_sib)
+k_stats_big_fast(const LevelDev* __restrict__ lvp, SegLevel sg, const u32* __restrict__ big_list,
+                 const u32* __restrict__ chunk_first, const u32* __restrict__ perm, const i64* __restrict__ pid,
+                 const float* __restrict__ rows, int ld, int dims, float qk, double qinv, int mx, StatsOut out,
+                 u64* __restrict__ gacc, int allow_whole, u32 keep_thr, const u32* __restrict__ bl_sib)
 {
+  if (blockIdx.x >= lvp->chunks) return;  // the grid is a host-side bound
+  const u32 nbig = lvp->nbig;
   constexpr int NT = 256 / TS;          // teams per CTA
   constexpr int PD = TS * CH * 4;       // dims per pass
   static_assert(VI_CHUNK / NT < VI_MAX_ROWS_PER_LANE, "a lane's 64-bit S2 accumulator would overflow");
@@ -454,50 +458,46 @@ k_stats_big_fast(SegLevel sg, const u32* __restrict__ big_list, const u32* __res
   if (threadIdx.x == 2) atomicAdd(&g[(size_t)ld * 3 + 2], (u64)m);  // local point count of this chunk
 }
 
-// Sibling derivation: sums of a derived range = the parent's (previous level's gacc) - its sibling's (this level's);
-// all words are exact integer sums (S1, the two S2 limbs, the id-sum halves, the count), so the difference is exact.
+// Sibling derivation + split choice of the big ranges, one warp per big-list slot.
+// A derived range's sums = the parent's (previous level's gacc) - its sibling's (this level's): all words are exact
+// integer sums (S1, the two S2 limbs, the id-sum halves, the count), so the difference is exact; they are stored in
+// this level's gacc (the range's own children may be derived from them) and the split is chosen from them.
+// Other ranges: arg-max over gacc, unless their single chunk CTA has already finished them.
 __global__ void __launch_bounds__(256)
-k_derive_big(u64* __restrict__ gacc, const u64* __restrict__ gacc_prev, const u32* __restrict__ bl_parent,
-             const u32* __restrict__ bl_sib, u32 nbig, u32 gstride)
-{
-  const u32 slot = blockIdx.x;
-  if (slot >= nbig) return;
-  const u32 par = bl_parent[slot];
-  if (par == 0xffffffffu) return;
-  const u64* gp = gacc_prev + (size_t)par * gstride;
-  const u64* gs = gacc + (size_t)bl_sib[slot] * gstride;
-  u64* g = gacc + (size_t)slot * gstride;
-  const u32 nd = (gstride - 3) / 3;  // = ld
-  for (u32 d = threadIdx.x; d < nd; d += 256)
-  {
-    g[d * 3 + 0] = gp[d * 3 + 0] - gs[d * 3 + 0];  // S1 (two's complement)
-    // S2 = limb0 + limb1 * 2^32; the limbs are sums of 32-bit pieces of the lanes' partial sums, not a canonical
-    // split, so the difference is taken on the 128-bit values and stored as (low 32 bits, the rest)
-    const unsigned __int128 sp = (unsigned __int128)gp[d * 3 + 1] + ((unsigned __int128)gp[d * 3 + 2] << 32);
-    const unsigned __int128 ss = (unsigned __int128)gs[d * 3 + 1] + ((unsigned __int128)gs[d * 3 + 2] << 32);
-    const unsigned __int128 sd = sp - ss;
-    g[d * 3 + 1] = (u64)(sd & 0xffffffffull);
-    g[d * 3 + 2] = (u64)(sd >> 32);
-  }
-  if (threadIdx.x < 3) g[nd * 3 + threadIdx.x] = gp[nd * 3 + threadIdx.x] - gs[nd * 3 + threadIdx.x];  // id sums, count
-}
-
-// warp per big range that spans several chunks (or column passes), or whose sums were derived: arg-max over gacc
-__global__ void __launch_bounds__(256)
-k_finalize_big_fast(SegLevel sg, const u32* __restrict__ big_list, u32 nbig, const u64* __restrict__ gacc, int ld,
-                    int dims, double qinv, int mx, StatsOut out, const float* __restrict__ rows,
-                    const u32* __restrict__ perm, int single_pass, int shared, u32* __restrict__ err,
-                    const u32* __restrict__ bl_parent)
+k_finalize_big_fast(const LevelDev* __restrict__ lvp, SegLevel sg, const u32* __restrict__ big_list, u64* __restrict__ gacc,
+                    const u64* __restrict__ gacc_prev, int ld, int dims, double qinv, int mx, StatsOut out,
+                    const float* __restrict__ rows, const u32* __restrict__ perm, int single_pass, int shared,
+                    u32* __restrict__ err, const u32* __restrict__ bl_parent, const u32* __restrict__ bl_sib)
 {
   const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= nbig) return;
+  if (warp >= lvp->nbig) return;
   const u32 s = big_list[warp];
-  const u64* g = gacc + (size_t)warp * ((size_t)ld * 3 + 3);
+  const size_t gstride = (size_t)ld * 3 + 3;
+  u64* g = gacc + (size_t)warp * gstride;
+  const u32 par = bl_parent != nullptr ? bl_parent[warp] : 0xffffffffu;
+  const bool derived = par != 0xffffffffu;
+  if (derived)
+  {
+    const u64* gp = gacc_prev + (size_t)par * gstride;
+    const u64* gs = gacc + (size_t)bl_sib[warp] * gstride;
+    for (int d = lane; d < ld; d += 32)
+    {
+      g[d * 3 + 0] = gp[d * 3 + 0] - gs[d * 3 + 0];  // S1 (two's complement)
+      // S2 = limb0 + limb1 * 2^32; the limbs are sums of 32-bit pieces of the lanes' partial sums, not a canonical
+      // split, so the difference is taken on the 128-bit values and stored as (low 32 bits, the rest)
+      const unsigned __int128 sp = (unsigned __int128)gp[d * 3 + 1] + ((unsigned __int128)gp[d * 3 + 2] << 32);
+      const unsigned __int128 ss = (unsigned __int128)gs[d * 3 + 1] + ((unsigned __int128)gs[d * 3 + 2] << 32);
+      const unsigned __int128 sd = sp - ss;
+      g[d * 3 + 1] = (u64)(sd & 0xffffffffull);
+      g[d * 3 + 2] = (u64)(sd >> 32);
+    }
+    if (lane < 3) g[(size_t)ld * 3 + lane] = gp[(size_t)ld * 3 + lane] - gs[(size_t)ld * 3 + lane];  // id sums, count
+    __syncwarp();
+  }
   // shared phase of a multi-rank build: n is the all-reduced (global) count and the float32 fallback, which needs
   // the range's rows in global order, is not available: a poorly resolved range is reported as an error
   const u32 n = shared ? (u32)g[(size_t)ld * 3 + 2] : sg.count[s];
-  const bool derived = bl_parent != nullptr && bl_parent[warp] != 0xffffffffu;
   if (!shared && single_pass && n <= VI_CHUNK && !derived) return;  // finished by its chunk CTA
   finalize_big_range(sg, s, n, g, g + (size_t)ld * 3, ld, dims, qinv, mx, out, rows, perm, lane, shared ? err : nullptr);
 }

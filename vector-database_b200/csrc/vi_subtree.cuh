@@ -18,15 +18,6 @@
 #include "vi_stats_exact.cuh"
 #include "vi_stats_fast.cuh"
 
-struct SubList  // device arrays, one entry per sub-tree root
-{
-  u32* start;  // first position in the sub-tree position space (sub_perm / sub_pid)
-  u32* count;
-  i64* rid;
-  u32* row;
-  u32* depth;
-};
-
 // RN(1/c) for the counts a sub-tree can see (host constant folding is IEEE division): the float32 fallback divides
 // through div_by_count (vi_stats_exact.cuh) instead of __fdiv_rn
 __constant__ float c_rcp32[33] = {

@@ -139,7 +139,7 @@ int vi_search_topk_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float p
   {
     rc = vi_search_impl(ctx, d_queries, nq, proximity, ctx->off_buf, ctx->ids_buf, cand, &cand, nullptr, true);
     if (rc != VI_OK) { cleanup(); return rc; }
-    k_candidate_distance<<<(u32)((cand + 127) / 128), 128, 0, st>>>(ctx->own_rows ? ctx->own_rows : ctx->rows, ctx->ld, ctx->dims,
+    k_candidate_distance<<<(u32)((cand + 127) / 128), 128, 0, st>>>(ctx->src_rows, ctx->ld, ctx->dims,
                                                                     d_queries, ctx->dims, ctx->off_buf, (u32)nq,
                                                                     ctx->search_src, cand, metric, d_dist, d_idx);
     size_t tmp_bytes = 0;
