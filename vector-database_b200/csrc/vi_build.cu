@@ -388,16 +388,22 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   // range-size classes (see vi_stats_fast.cuh / vi_stats_exact.cuh); defaults from scripts/sweep.py on 10M x 96
   // (profiles/r1_sweep.txt); the variables exist for such sweeps
   env.t_team = env_u32("VI_B200_T_TEAM", 32, 2, VI_MAX_ROWS_PER_LANE);
-  const u32 t_big_fast = env_u32("VI_B200_T_BIG", 512, VI_MIN_BIG, VI_MAX_ROWS_PER_LANE);
+  const u32 t_big_fast = env_u32("VI_B200_T_BIG", 512, VI_MIN_BIG, VI_MAX_ROWS_PER_LANE);  // raised to t_sub + 1 below
   const u32 t_big_exact = env_u32("VI_B200_T_BIG_EXACT", 512, VI_MIN_BIG, 1u << 30);
   env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
   env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 8, 0, 8);  // 0 = cp.async ring
   env.sibling = env_u32("VI_B200_SIBLING", 1, 0, 1);
-  // sub-tree kernel (fast mode): as many rows as fit 12 KB of shared memory per warp, at most 32 (one point per lane)
-  u32 sub_rows = std::min<u32>(32u, (u32)(12288 / (ctx->ld * 4)));
-  if (sub_rows < 4 || mode != VI_MODE_FAST || ctx->ld > 128) sub_rows = 0;  // wider rows stay on the level path
-  env.t_sub = std::min(env_u32("VI_B200_T_SUB", sub_rows, 0, 32), sub_rows);
-  env.sub_minb = env_u32("VI_B200_SUB_MINB", 2, 2, 3);
+  // sub-tree kernel (fast mode, vi_subtree.cuh): a range of up to t_sub points is finished by one CTA in shared
+  // memory; t_sub = as many points as fit next to the kernel's static shared memory, at most SUB_TMAX
+  {
+    const size_t budget = (227u * 1024u) / (512 / SUB_NT) - 5120u;  // per resident CTA, minus the kernel's static shared memory
+    const size_t per_point = sub_smem_bytes(1, ctx->ld);
+    u32 sub_rows = (u32)std::min<size_t>((size_t)SUB_TMAX, budget / per_point) & ~31u;
+    if (sub_rows < 32 || mode != VI_MODE_FAST) sub_rows = 0;  // very wide rows stay on the level path
+    env.t_sub = std::min(env_u32("VI_B200_T_SUB", sub_rows, 0, (u32)SUB_TMAX) & ~31u, sub_rows);
+  }
+  env.sub_minb = 1;
+  if (env.t_sub + 1 > env.t_big) env.t_big = env.t_sub + 1;  // whatever does not go to a sub-tree is a big range
   // The host enqueues level l+1 before it has read level l's record back (the kernels take their sizes from the
   // device-resident record, the grids from bounds derived from the last record the host knows).  The exact mode's
   // kernels are launched on exact sizes (its top levels are latency-bound chains anyway): no run-ahead there.
@@ -489,42 +495,23 @@ static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* 
   VI_CUDA_TRY(cudaMemsetAsync(ctx->sub_stats, 0, 160 * 8, st));
   TableOut tout{ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high};
   SubList sl{ctx->sub_start, ctx->sub_count, ctx->sub_rid, ctx->sub_row, ctx->sub_depth};
-  const size_t smem = (size_t)SUB_WARPS * rows_max * ld * sizeof(float);
-  const u32 grid = std::min<u32>((s.sub_cnt + SUB_WARPS - 1) / SUB_WARPS, (u32)VI_NUM_SMS * 8 * env.sub_minb);
+  const size_t smem = sub_smem_bytes(rows_max, ld);
+  const u32 grid = std::min<u32>(s.sub_cnt, (u32)VI_NUM_SMS * (512 / SUB_NT));  // persistent CTAs over a work cursor
   cudaEvent_t e0 = env_event(ctx, env);
-#define CALL_SUB2(CH, MINB)                                                                                                 \
-  do                                                                                                                        \
-  {                                                                                                                         \
-    if (sub_full)                                                                                                           \
-    {                                                                                                                       \
-      VI_CUDA_TRY(cudaFuncSetAttribute(k_subtree_fast<CH, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                       (int)smem));                                                                         \
-      k_subtree_fast<CH, MINB, true><<<grid, SUB_WARPS * 32, smem, st>>>(                                                   \
-          sl, s.sub_cnt, ctx->sub_perm, ctx->sub_pid, rows, ld, dims, env.qk, env.qinv, tout, ctx->t_src, row_base,         \
-          overflow_base, (u32)ctx->t_cap, cnt, lvlp, lvlr, rows_max);                                                       \
-    }                                                                                                                       \
-    else                                                                                                                    \
-    {                                                                                                                       \
-      VI_CUDA_TRY(cudaFuncSetAttribute(k_subtree_fast<CH, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                       (int)smem));                                                                         \
-      k_subtree_fast<CH, MINB, false><<<grid, SUB_WARPS * 32, smem, st>>>(                                                  \
-          sl, s.sub_cnt, ctx->sub_perm, ctx->sub_pid, rows, ld, dims, env.qk, env.qinv, tout, ctx->t_src, row_base,         \
-          overflow_base, (u32)ctx->t_cap, cnt, lvlp, lvlr, rows_max);                                                       \
-    }                                                                                                                       \
+#define CALL_SUB(CH, FULL)                                                                                                \
+  do                                                                                                                      \
+  {                                                                                                                       \
+    VI_CUDA_TRY(cudaFuncSetAttribute(k_subtree_cta<CH, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    k_subtree_cta<CH, FULL><<<grid, SUB_NT, smem, st>>>(sl, s.sub_cnt, ctx->sub_perm, ctx->sub_pid, rows, ld, dims, env.qk, \
+                                                        env.qinv, tout, ctx->t_src, row_base, overflow_base,              \
+                                                        (u32)ctx->t_cap, cnt, lvlp, lvlr, rows_max);                      \
   } while (0)
-#define CALL_SUB(CH)                                  \
-  do                                                  \
-  {                                                   \
-    if (env.sub_minb >= 3) CALL_SUB2(CH, 3);          \
-    else CALL_SUB2(CH, 2);                            \
-  } while (0)
-  const bool sub_full = (ld % 32 == 0) && dims == ld;
-  const int ch = (ld / 4 + 7) / 8;  // float4 chunks per team lane (rows up to 128 floats wide, see env_init)
-  if (ch <= 1) CALL_SUB(1);
-  else if (ch == 2) CALL_SUB(2);
-  else if (ch == 3) CALL_SUB(3);
-  else CALL_SUB(4);
-#undef CALL_SUB2
+  const int ch = std::min(4, (ld / 4 + 7) / 8);  // int4 columns per team lane and pass
+  const bool sub_full = ld == 32 * ch && dims == ld;
+  if (ch <= 1) { if (sub_full) CALL_SUB(1, true); else CALL_SUB(1, false); }
+  else if (ch == 2) { if (sub_full) CALL_SUB(2, true); else CALL_SUB(2, false); }
+  else if (ch == 3) { if (sub_full) CALL_SUB(3, true); else CALL_SUB(3, false); }
+  else { if (sub_full) CALL_SUB(4, true); else CALL_SUB(4, false); }
 #undef CALL_SUB
   ++env.launches;
   cudaEvent_t e1 = env_event(ctx, env);
@@ -533,12 +520,25 @@ static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* 
   VI_CUDA_TRY(cudaStreamSynchronize(st));
   VI_CUDA_TRY(cudaGetLastError());
   const u32 overflow = (u32)(h[128] & 0xffffffffu), err = (u32)(h[128] >> 32);
-  if (getenv("VI_B200_TRACE")) fprintf(stderr, "[vi_b200] sub-trees %u, float32 fallbacks %u, overflow rows %u\n", s.sub_cnt,
-                                       (u32)(h[129] & 0xffffffffu), overflow);
+  if (getenv("VI_B200_TRACE"))
+  {
+    fprintf(stderr, "[vi_b200] sub-trees %u, float32 fallbacks %u, overflow rows %u\n", s.sub_cnt, (u32)(h[129] & 0xffffffffu),
+            overflow);
+    unsigned long long dbg[8] = {};
+    cudaMemcpyFromSymbol(dbg, g_sub_dbg, sizeof(dbg));
+    if (dbg[3])
+      fprintf(stderr, "[vi_b200] sub-tree kernel, thread 0 cycles per sub-tree: load %.0f, phase 1 %.0f, phase 2 %.0f (%llu sub-trees); "
+              "phase 1: CTA-wide nodes %.0f cycles (%.2f nodes), warp nodes %.0f cycles (%.2f nodes)\n",
+              (double)dbg[0] / dbg[3], (double)dbg[1] / dbg[3], (double)dbg[2] / dbg[3], dbg[3], (double)dbg[4] / dbg[3],
+              (double)dbg[6] / dbg[3], (double)dbg[5] / dbg[3], (double)dbg[7] / dbg[3]);
+    unsigned long long z[8] = {};
+    cudaMemcpyToSymbol(g_sub_dbg, z, sizeof(z));
+  }
   if (err == 1) return ctx->fail(VI_ERR_CAPACITY, "range table capacity exceeded (degenerate input: too many one-child ranges)");
   if (err == 2)
     return ctx->fail(VI_ERR_OVERFLOW, "rangeId overflow: a range at depth 62 still holds more than one point "
                                       "(IndexBuilder.cs:99 checked(rangeId * 2 + 1))");
+  if (err != 0) return ctx->fail(VI_ERR_STATE, "sub-tree kernel: internal error (node queue stalled)");
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   ctx->info.subtree_ms += ms;

@@ -16,7 +16,7 @@ typedef unsigned __int128 u128;
 
 // Ranges with at least t_big points are "big": their statistics are computed by many CTAs (fast mode) or by one
 // thread per (range, dimension) chain (exact mode); smaller ranges are owned by one team/warp (vi_build.cu).
-constexpr u32 VI_MIN_BIG = 512;  // smallest allowed "big range" threshold (sizes the big-range work space)
+constexpr u32 VI_MIN_BIG = 256;  // smallest allowed "big range" threshold (sizes the big-range work space)
 // Rows of a big range handled by one CTA of the fast-mode statistics kernel.
 constexpr u32 VI_CHUNK = 4096;
 constexpr int VI_NUM_SMS = 148;
