@@ -393,17 +393,14 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
   env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 8, 0, 8);  // 0 = cp.async ring
   env.sibling = env_u32("VI_B200_SIBLING", 1, 0, 1);
-  // sub-tree kernel (fast mode, vi_subtree.cuh): a range of up to t_sub points is finished by one CTA in shared
-  // memory; t_sub = as many points as fit next to the kernel's static shared memory, at most SUB_TMAX
+  // sub-tree kernel (fast mode, vi_subtree.cuh): a range of up to t_sub points is finished by one warp in shared
+  // memory; as many rows as fit 12.5 KB per warp (8 warps per CTA, 2 CTAs per SM), at most 32 (one point per lane)
   {
-    const size_t budget = (227u * 1024u) / (512 / SUB_NT) - 5120u;  // per resident CTA, minus the kernel's static shared memory
-    const size_t per_point = sub_smem_bytes(1, ctx->ld);
-    u32 sub_rows = (u32)std::min<size_t>((size_t)SUB_TMAX, budget / per_point) & ~31u;
-    if (sub_rows < 32 || mode != VI_MODE_FAST) sub_rows = 0;  // very wide rows stay on the level path
-    env.t_sub = std::min(env_u32("VI_B200_T_SUB", sub_rows, 0, (u32)SUB_TMAX) & ~31u, sub_rows);
+    u32 sub_rows = std::min<u32>((u32)SUB_TMAX, (u32)(12800 / (ctx->ld * 4 + 16)));
+    if (sub_rows < 4 || mode != VI_MODE_FAST) sub_rows = 0;  // wide rows stay on the level path
+    env.t_sub = std::min(env_u32("VI_B200_T_SUB", sub_rows, 0, (u32)SUB_TMAX), sub_rows);
   }
-  env.sub_minb = 1;
-  if (env.t_sub + 1 > env.t_big) env.t_big = env.t_sub + 1;  // whatever does not go to a sub-tree is a big range
+  env.sub_minb = 2;
   // The host enqueues level l+1 before it has read level l's record back (the kernels take their sizes from the
   // device-resident record, the grids from bounds derived from the last record the host knows).  The exact mode's
   // kernels are launched on exact sizes (its top levels are latency-bound chains anyway): no run-ahead there.
@@ -495,16 +492,17 @@ static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* 
   VI_CUDA_TRY(cudaMemsetAsync(ctx->sub_stats, 0, 160 * 8, st));
   TableOut tout{ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high};
   SubList sl{ctx->sub_start, ctx->sub_count, ctx->sub_rid, ctx->sub_row, ctx->sub_depth};
-  const size_t smem = sub_smem_bytes(rows_max, ld);
-  const u32 grid = std::min<u32>(s.sub_cnt, (u32)VI_NUM_SMS * (512 / SUB_NT));  // persistent CTAs over a work cursor
+  const size_t smem = (size_t)SUB_WARPS * sub_smem_bytes_per_warp(rows_max, ld);
+  const u32 grid = std::min<u32>((s.sub_cnt + SUB_WARPS - 1) / SUB_WARPS, (u32)VI_NUM_SMS * 2u);  // persistent warps, work cursor
   cudaEvent_t e0 = env_event(ctx, env);
 #define CALL_SUB(CH, FULL)                                                                                                \
   do                                                                                                                      \
   {                                                                                                                       \
-    VI_CUDA_TRY(cudaFuncSetAttribute(k_subtree_cta<CH, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    k_subtree_cta<CH, FULL><<<grid, SUB_NT, smem, st>>>(sl, s.sub_cnt, ctx->sub_perm, ctx->sub_pid, rows, ld, dims, env.qk, \
-                                                        env.qinv, tout, ctx->t_src, row_base, overflow_base,              \
-                                                        (u32)ctx->t_cap, cnt, lvlp, lvlr, rows_max);                      \
+    VI_CUDA_TRY(cudaFuncSetAttribute(k_subtree_fast<CH, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    k_subtree_fast<CH, FULL><<<grid, SUB_WARPS * 32, smem, st>>>(sl, s.sub_cnt, ctx->sub_perm, ctx->sub_pid, rows, ld, dims, \
+                                                                 env.qk, env.qinv, tout, ctx->t_src, row_base,            \
+                                                                 overflow_base, (u32)ctx->t_cap, cnt, lvlp, lvlr,         \
+                                                                 rows_max);                                               \
   } while (0)
   const int ch = std::min(4, (ld / 4 + 7) / 8);  // int4 columns per team lane and pass
   const bool sub_full = ld == 32 * ch && dims == ld;
@@ -524,15 +522,6 @@ static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* 
   {
     fprintf(stderr, "[vi_b200] sub-trees %u, float32 fallbacks %u, overflow rows %u\n", s.sub_cnt, (u32)(h[129] & 0xffffffffu),
             overflow);
-    unsigned long long dbg[8] = {};
-    cudaMemcpyFromSymbol(dbg, g_sub_dbg, sizeof(dbg));
-    if (dbg[3])
-      fprintf(stderr, "[vi_b200] sub-tree kernel, thread 0 cycles per sub-tree: load %.0f, phase 1 %.0f, phase 2 %.0f (%llu sub-trees); "
-              "phase 1: CTA-wide nodes %.0f cycles (%.2f nodes), warp nodes %.0f cycles (%.2f nodes)\n",
-              (double)dbg[0] / dbg[3], (double)dbg[1] / dbg[3], (double)dbg[2] / dbg[3], dbg[3], (double)dbg[4] / dbg[3],
-              (double)dbg[6] / dbg[3], (double)dbg[5] / dbg[3], (double)dbg[7] / dbg[3]);
-    unsigned long long z[8] = {};
-    cudaMemcpyToSymbol(g_sub_dbg, z, sizeof(z));
   }
   if (err == 1) return ctx->fail(VI_ERR_CAPACITY, "range table capacity exceeded (degenerate input: too many one-child ranges)");
   if (err == 2)
