@@ -119,19 +119,70 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def gen_device(n, dims, seed, device):
-    """unit-normalised Gaussian rows generated on the GPU (torch is plumbing: device memory + RNG)."""
+GEN_CHUNK = 1 << 20
+
+
+def gen_device(n, dims, seed, device, lo=0, hi=None):
+    """Rows [lo, hi) of THE synthetic data set of n unit-normalised Gaussian rows, generated on the GPU (torch is
+    plumbing: device memory + RNG).  Every 2^20-row chunk has its own seed, so a rank's shard is a slice of exactly the
+    rows a single-GPU run generates: the multi-GPU builds index the same points for every GPU count."""
     import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    rows = torch.empty((n, dims), dtype=torch.float32, device=device)
-    chunk = 1 << 20
-    for s in range(0, n, chunk):
-        e = min(n, s + chunk)
+    hi = n if hi is None else hi
+    rows = torch.empty((hi - lo, dims), dtype=torch.float32, device=device)
+    for c in range(lo // GEN_CHUNK, (hi + GEN_CHUNK - 1) // GEN_CHUNK):
+        s, e = c * GEN_CHUNK, min(n, (c + 1) * GEN_CHUNK)
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 1000003 + c)
         x = torch.randn((e - s, dims), generator=g, device=device, dtype=torch.float32)
-        rows[s:e] = x / x.norm(dim=1, keepdim=True)
-    ids = torch.arange(n, dtype=torch.int64, device=device)
+        x = x / x.norm(dim=1, keepdim=True)
+        a, b = max(s, lo), min(e, hi)
+        rows[a - lo:b - lo] = x[a - s:b - s]
+    ids = torch.arange(lo, hi, dtype=torch.int64, device=device)
     return ids, rows
+
+
+def table_checksum(rid, dim, mid, oid):
+    """Order-independent 64-bit hash of the rows (RangeID, Dimension, Mid bits, Id): equal for equal tables whatever
+    the row order, the GPU count or the rank that produced a row."""
+    with np.errstate(over="ignore"):
+        x = (rid.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+             + dim.astype(np.int64).astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
+             + mid.view(np.uint32).astype(np.uint64) * np.uint64(0x165667B19E3779F9)
+             + oid.astype(np.uint64) * np.uint64(0xD6E8FEB86659FD93))
+        x ^= x >> np.uint64(29)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(32)
+        return f"{int(x.sum(dtype=np.uint64)):016x}-{len(rid)}"
+
+
+def divergence(fast, exact, scale):
+    """Fast-mode table against the literal (reference-arithmetic) table of the same points."""
+    fr, fd, fm, fo = fast
+    er, ed, em, eo = exact
+    o = np.argsort(fr, kind="stable")
+    fr, fd, fm, fo = fr[o], fd[o], fm[o], fo[o]
+    o = np.argsort(er, kind="stable")
+    er, ed, em, eo = er[o], ed[o], em[o], eo[o]
+    common, fi, ei = np.intersect1d(fr, er, assume_unique=True, return_indices=True)
+    same_dim = fd[fi] == ed[ei]
+    identical = same_dim & (fm[fi].view(np.uint32) == em[ei].view(np.uint32)) & (fo[fi] == eo[ei])
+    internal = same_dim & (fd[fi] >= 0)
+    dmid = np.abs(fm[fi][internal].astype(np.float64) - em[ei][internal].astype(np.float64))
+    top = internal & (common < 2 ** 10 - 1)  # levels 0..9: ranges of ~10k points and more
+    dtop = np.abs(fm[fi][top].astype(np.float64) - em[ei][top].astype(np.float64))
+    fl, el = fd == -1, ed == -1
+    same_path = float((fr[fl][np.argsort(fo[fl])] == er[el][np.argsort(eo[el])]).mean())
+    lvl = np.floor(np.log2(common[~same_dim].astype(np.float64) + 1)).astype(np.int64) if (~same_dim).any() else np.array([0])
+    return {"rows_exact": int(len(er)), "rows_fast": int(len(fr)), "rows_in_both": int(len(common)),
+            "same_dimension": int(same_dim.sum()), "bit_identical_rows": int(identical.sum()),
+            "max_abs_dmid_over_scale_levels_0_9": float(dtop.max() / scale) if dtop.size else 0.0,
+            "max_abs_dmid_over_scale_all_common": float(dmid.max() / scale) if dmid.size else 0.0,
+            "first_level_with_a_different_dimension": int(lvl.min()) if (~same_dim).any() else None,
+            "points_with_the_same_root_to_leaf_path": same_path, "scale_max_abs_x": scale,
+            "note": "exact = literal float32 Welford (the reference's arithmetic), fast = qfx.  Deep in the tree a row "
+                    "with the same RangeID can hold a different point set once one point changed sides above it, so "
+                    "|dMid| over ALL common rows measures tree divergence, not arithmetic error; levels 0..9 show the "
+                    "arithmetic (the literal recurrence's own O(sqrt(n) ulp) drift)."}
 
 
 def gen_queries(rows_d, nq, seed):
@@ -192,17 +243,40 @@ def cpu_baseline(rows_h, ids_h, sample_rows):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (the oracle port; the C# original cannot run here: no .NET)."""
+    """--impl reference: the reference's CPU algorithm (the oracle port; the C# original cannot run here: no .NET) with
+    every host thread it can use, on the SAME config as the GPU arm when the time budget allows: a calibration build of
+    1M rows is extrapolated with n*log2(n); if warmup + steps full-size builds fit `--ref-budget-s` the sample is the
+    whole workload, otherwise the largest row count that fits (the extrapolation to the full size is printed beside it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from vectorindex import synthetic as ds
     import oracle
-    n = args.ref_rows
-    ids, rows = ds.unit_gaussian(n, DIMS, seed=SEED)
+    full = args.rows
+    ids, rows = ds.unit_gaussian(full if args.ref_rows <= 0 else min(full, args.ref_rows), DIMS, seed=SEED)
     threads = pick_threads(ids, rows)
+    cal_n = min(1_000_000, rows.shape[0])
+    t0 = time.perf_counter()
+    oracle.build_mt(ids[:cal_n], rows[:cal_n], threads)
+    cal_s = time.perf_counter() - t0
+    nlogn = lambda m: m * np.log2(max(m, 2))
+    est_full = cal_s * nlogn(full) / nlogn(cal_n)
+    builds = args.warmup + args.steps
+    n = rows.shape[0]
+    if est_full * builds > args.ref_budget_s:
+        lo_n, hi_n = cal_n, n
+        while hi_n - lo_n > 50_000:  # largest n whose builds fit the budget
+            m = (lo_n + hi_n) // 2
+            if cal_s * nlogn(m) / nlogn(cal_n) * builds <= args.ref_budget_s:
+                lo_n = m
+            else:
+                hi_n = m
+        n = max(cal_n, lo_n // 100_000 * 100_000)
+    log(f"[reference] {threads} threads; 1M-row build {cal_s:.2f} s -> {full}-row build ~{est_full:.1f} s; "
+        f"{builds} builds of {n} rows")
+    ids, rows = ids[:n], rows[:n]
     times = []
-    for i in range(args.warmup + args.steps):
+    for i in range(builds):
         t0 = time.perf_counter()
         tbl = oracle.build_mt(ids, rows, threads)
         dt = time.perf_counter() - t0
@@ -211,13 +285,18 @@ def run_reference(args):
         log(f"[reference] step {i}: {dt:.2f} s, {len(tbl)} ranges")
     ms = 1000.0 * sum(times) / len(times)
     v = n / (ms / 1000.0)
+    ext_ms = ms * nlogn(full) / nlogn(n)
     line = {"impl": "reference", "metric": "index_build_vectors_per_sec", "value": v, "unit": "vectors/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"deep-image-96-shaped synthetic {args.rows}x96 index build (IndexBuilder.Build)",
-                       "sample_rows": n, "mode": "literal float32 Welford (IndexBuilder.cs:175-197)", "threads": threads},
+            "config": {"workload": f"configs[1]: deep-image-96-angular-shaped synthetic {full}x{DIMS} index build "
+                                   f"(IndexBuilder.Build)",
+                       "sample_rows": n, "same_config": n == full,
+                       "mode": "literal float32 Welford (IndexBuilder.cs:175-197)", "threads": threads,
+                       "full_size_extrapolation": {"rows": full, "ms_per_step": ext_ms, "value": full / (ext_ms / 1e3),
+                                                   "how": "measured ms x (N log2 N) ratio"}},
             "cpu_baseline": {"value": v, "unit": "vectors/s", "cores": threads, "kind": "port",
-                             "sample": f"each step = one full literal build of a {n}-row sample of the workload "
+                             "sample": f"each step = one full literal build of {'the whole workload' if n == full else f'a {n}-row sample of the workload'} "
                                        f"(numpy seed {SEED}) with {threads} host threads (oracle/vi_oracle_mt.c; the "
                                        f"reference itself is sequential, its arithmetic is kept bit for bit)",
                              "host_cores_available": os.cpu_count()},
@@ -233,7 +312,7 @@ def run_multi(args, rank, world, local):
     import torch
     import torch.distributed as dist
     import vectorindex as vi
-    from vectorindex.distributed import Collectives
+    from vectorindex.distributed import Collectives, init_nccl
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -241,13 +320,15 @@ def run_multi(args, rank, world, local):
     n = args.rows
     lo, hi = rank * n // world, (rank + 1) * n // world
     m = hi - lo
-    ids_d, rows_d = gen_device(m, DIMS, SEED * 1000 + rank, dev)
-    ids_d += lo
+    ids_d, rows_d = gen_device(n, DIMS, SEED, dev, lo, hi)  # a slice of the very rows the 1-GPU run indexes
     ctx = vi.Context(local)
     ctx.reserve(m, DIMS)
     ctx.add_device(ids_d.data_ptr(), rows_d.data_ptr(), m, DIMS)
-    coll = Collectives(dev)
-    coll.attach(ctx)
+    if args.transport == "callbacks":
+        coll = Collectives(dev)   # torch.distributed behind vi_set_collective
+        coll.attach(ctx)
+    else:
+        init_nccl(ctx, dev)       # library-owned NCCL communicator, collectives on the library's stream
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def sync_all():
@@ -279,15 +360,17 @@ def run_multi(args, rank, world, local):
     stats_ms = sum(l.stats_ms for l in levels) + info.subtree_ms
     peak, peak_src = peaks()
 
-    # ---- search: replicate the table, shard the query batch (configs[3]) ------------------------------------------
+    calls_before = ctx.comm_stats()
+    # ---- replicate the table (checksum; search shards the query batch against it, configs[3]) --------------------------
+    sync_all()
+    t0 = time.perf_counter()
+    ctx.replicate()
+    sync_all()
+    trep = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+    dist.all_reduce(trep, op=dist.ReduceOp.MAX)
+    checksum = table_checksum(*ctx.ranges()) if rank == 0 else None
     search = None
     if not args.no_search:
-        sync_all()
-        t0 = time.perf_counter()
-        ctx.replicate()
-        sync_all()
-        trep = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
-        dist.all_reduce(trep, op=dist.ReduceOp.MAX)
         nq = args.queries // world
         q_d = gen_queries(rows_d, nq, seed=77 + rank)
         offs_d = torch.empty(nq + 1, dtype=torch.int64, device=dev)
@@ -324,7 +407,7 @@ def run_multi(args, rank, world, local):
     del rows_d, ids_d
     cap = 4 * m + 65536
     outs = [torch.empty(cap, dtype=dt, pin_memory=True).numpy() for dt in (torch.int64, torch.int32, torch.float32, torch.int64)]
-    e2e_ms = []
+    e2e_ms, own_ms = [], []
     k_rows = 0
     for i in range(2 + max(1, min(args.steps, 3))):
         sync_all()
@@ -333,9 +416,12 @@ def run_multi(args, rank, world, local):
         ctx.add(ids_h.numpy(), rows_h.numpy())
         ctx.build(vi.MODE_FAST)
         k_rows = ctx.ranges_into(*outs)
+        torch.cuda.synchronize()
+        dt_own = (time.perf_counter() - t0) * 1e3
         sync_all()
         if i >= 2:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
+            own_ms.append(dt_own)
     te = torch.tensor([sum(e2e_ms) / len(e2e_ms)], device=dev, dtype=torch.float64)
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
     d2h = torch.tensor([float(k_rows) * 24], device=dev, dtype=torch.float64)
@@ -350,9 +436,11 @@ def run_multi(args, rank, world, local):
                                          f"(per-level NCCL all-reduce of range statistics, one all-to-all to range owners)",
                              "mode": "fast (qfx)", "rows": n, "dims": DIMS, "rows_per_gpu": m,
                              "l2": "each rank's rows (%.2f GB) exceed the 126 MB L2" % (m * DIMS * 4 / 1e9),
-                             "ranges": int(stats[0].item()) + ctx.shared_rows, "shared_rows": ctx.shared_rows,
-                             "collectives_per_build": {k: v // (args.warmup + args.steps + len(e2e_ms) + 2)
-                                                       for k, v in coll.calls.items()}},
+                             "ranges": int(checksum.split("-")[1]), "table_checksum": checksum,
+                             "data_set": "rows [rank*N/G, (rank+1)*N/G) of the chunk-seeded N-row set the 1-GPU run indexes",
+                             "transport": args.transport,
+                             "collectives_per_build": {k: v // (args.warmup + args.steps)
+                                                       for k, v in calls_before.items()}},
                   "clocks": clocks, "gpu_launches": int(stats[1].item()),
                   "roofline": {"bound": "hbm", "kernel": "k_stats_big_fast + k_stats_small_fast on rank 0 (its shard / owned sub-trees)",
                                "achieved": stats_b / (stats_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -361,9 +449,9 @@ def run_multi(args, rank, world, local):
                                                      "partition_ms": sum(l.partition_ms for l in levels)}},
                   "e2e": {"value": n / (e2e / 1e3), "unit": "vectors/s", "ms_per_step": e2e,
                           "h2d_bytes_per_step": n * (4 * DIMS + 8), "d2h_bytes_per_step": int(d2h.item()),
-                          "steps": len(e2e_ms), "warmup": 2,
+                          "steps": len(e2e_ms), "warmup": 2, "rank0_ms_before_the_closing_barrier": sum(own_ms) / len(own_ms),
                           "path": "per rank: vi_points_reserve + vi_points_add(host pinned shard) + vi_build(fast, sharded) + vi_ranges_copy"},
-                  "search": search, "cpu_baseline": None}
+                  "replicate_ms": float(trep.item()), "search": search, "cpu_baseline": None}
         log(f"[{world} GPUs] build {ms_per_step:.2f} ms/step, e2e {e2e:.1f} ms/step; rank0 levels: "
             + str([(l.level, l.ranges, l.points, round(l.stats_ms, 2), round(l.partition_ms, 2)) for l in levels]))
         emit(result)
@@ -380,10 +468,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dims", type=int, default=96, help="96 = BASELINE configs[1]; 768 with --rows 1000000 = configs[4]")
-    ap.add_argument("--ref-rows", type=int, default=1_000_000)
+    ap.add_argument("--ref-rows", type=int, default=0, help="--impl reference: cap on the sample rows (0 = the whole workload "
+                    "if it fits --ref-budget-s)")
+    ap.add_argument("--ref-budget-s", type=float, default=420.0, help="--impl reference: seconds all its builds may take")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
     ap.add_argument("--queries", type=int, default=1_000_000)
     ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "callbacks"], help="multi-GPU: library-owned NCCL "
+                    "(vi_comm_init) or the host's torch.distributed behind vi_set_collective")
     ap.add_argument("--no-exact", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -489,17 +581,31 @@ def main():
                          "ranges": int(info.ranges), "levels": int(info.levels)},
               "clocks": clocks, "gpu_launches": int(info.kernel_launches), "roofline": roofline}
 
+    scale = float(rows_d.abs().max().item())
+    fast_table = ctx.ranges()
+    result["config"]["table_checksum"] = table_checksum(*fast_table)
     # ---- exact mode (bit-identical to the reference) -------------------------------------------------------------
     if not args.no_exact:
         ems, einfos, _ = timed_builds(vi.MODE_EXACT, 1, 2)
         e_ms = sum(ems) / len(ems)
+        elv = ctx.levels()
         result["exact_mode"] = {"value": n / (e_ms / 1e3), "unit": "vectors/s", "ms_per_step": e_ms, "steps": 2, "warmup": 1,
                                 "note": "literal float32 sequential Welford (IndexBuilder.cs:175-197), bit-identical range table; "
                                         "latency-bound by the per-(range,dim) recurrence at the top levels",
-                                "gpu_launches": int(einfos[-1].kernel_launches)}
+                                "gpu_launches": int(einfos[-1].kernel_launches),
+                                "per_level": [{"level": l.level, "ranges": l.ranges, "points": l.points,
+                                               "stats_ms": round(l.stats_ms, 4), "partition_ms": round(l.partition_ms, 4)}
+                                              for l in elv]}
         log(f"exact build: {e_ms:.2f} ms/step; per level (ranges, points, stats_ms, partition_ms): "
-            + str([(l.ranges, l.points, round(l.stats_ms, 2), round(l.partition_ms, 2)) for l in ctx.levels()]))
+            + str([(l.ranges, l.points, round(l.stats_ms, 2), round(l.partition_ms, 2)) for l in elv]))
+        exact_table = ctx.ranges()
+        result["exact_mode"]["table_checksum"] = table_checksum(*exact_table)
+        t0 = time.perf_counter()
+        result["divergence"] = divergence(fast_table, exact_table, scale)
+        log(f"divergence fast vs exact ({time.perf_counter() - t0:.1f} s): {result['divergence']}")
+        del exact_table
         ctx.build(vi.MODE_FAST)
+    del fast_table
 
     # ---- search ---------------------------------------------------------------------------------------------------
     if not args.no_search:
@@ -549,31 +655,60 @@ def main():
     out_mid = torch.empty(cap, dtype=torch.float32, pin_memory=True).numpy()
     out_id = torch.empty(cap, dtype=torch.int64, pin_memory=True).numpy()
     ctx = vi.Context(local)
-    e2e_ms = []
-    k_rows = 0
-    for i in range(2 + max(1, min(args.steps, 3))):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ctx.reserve(n, DIMS)
-        t1 = time.perf_counter()
-        ctx.add(ids_np, rows_np)
-        t2 = time.perf_counter()
-        ctx.build(vi.MODE_FAST)
-        t3 = time.perf_counter()
-        k_rows = ctx.ranges_into(out_rid, out_dim, out_mid, out_id)
-        torch.cuda.synchronize()
-        t4 = time.perf_counter()
-        dt = (t4 - t0) * 1e3
-        log(f"e2e step {i}: reserve {1e3*(t1-t0):.1f} add(H2D) {1e3*(t2-t1):.1f} build {1e3*(t3-t2):.1f} "
-            f"ranges_copy(D2H) {1e3*(t4-t3):.1f} ms")
-        if i >= 2:
-            e2e_ms.append(dt)
-    e2e = sum(e2e_ms) / len(e2e_ms)
+
+    def e2e_builds(mode, steps, warm=2):
+        ms_list, k_rows = [], 0
+        for i in range(warm + steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.reserve(n, DIMS)
+            t1 = time.perf_counter()
+            ctx.add(ids_np, rows_np)
+            t2 = time.perf_counter()
+            ctx.build(mode)
+            t3 = time.perf_counter()
+            k_rows = ctx.ranges_into(out_rid, out_dim, out_mid, out_id)
+            torch.cuda.synchronize()
+            t4 = time.perf_counter()
+            dt = (t4 - t0) * 1e3
+            log(f"e2e mode {mode} step {i}: reserve {1e3*(t1-t0):.1f} add(H2D) {1e3*(t2-t1):.1f} build {1e3*(t3-t2):.1f} "
+                f"ranges_copy(D2H) {1e3*(t4-t3):.1f} ms")
+            if i >= warm:
+                ms_list.append(dt)
+        return sum(ms_list) / len(ms_list), len(ms_list), k_rows
+
+    e2e, e2e_steps, k_rows = e2e_builds(vi.MODE_FAST, max(1, min(args.steps, 3)))
     result["e2e"] = {"value": n / (e2e / 1e3), "unit": "vectors/s", "ms_per_step": e2e,
                      "h2d_bytes_per_step": n * (4 * DIMS + 8), "d2h_bytes_per_step": int(k_rows) * 24,
-                     "steps": len(e2e_ms), "warmup": 2,
+                     "steps": e2e_steps, "warmup": 2,
                      "path": "vi_points_reserve + vi_points_add(host pinned) + vi_build(fast) + vi_ranges_copy(host pinned)"}
     log(f"e2e: {e2e:.1f} ms/step")
+    if not args.no_exact:
+        xe, xs, xk = e2e_builds(vi.MODE_EXACT, 2, warm=1)
+        result["exact_mode"]["e2e"] = {"value": n / (xe / 1e3), "unit": "vectors/s", "ms_per_step": xe,
+                                       "h2d_bytes_per_step": n * (4 * DIMS + 8), "d2h_bytes_per_step": int(xk) * 24,
+                                       "steps": xs, "warmup": 1,
+                                       "path": "vi_points_reserve + vi_points_add(host pinned) + vi_build(exact) + vi_ranges_copy"}
+        log(f"exact e2e: {xe:.1f} ms/step")
+        ctx.build(vi.MODE_FAST)
+    if not args.no_search:
+        # search through the plugin call with HOST buffers: queries H2D, traversal (count + fill), offsets and ids D2H
+        rng = np.random.default_rng(77)
+        se = {}
+        for p, nqe in ((0.0, min(args.queries, 1_000_000)), (0.01, min(args.queries, 200_000))):
+            pick = rng.integers(0, n, nqe // 2)
+            fresh = rng.standard_normal((nqe - nqe // 2, DIMS), dtype=np.float32)
+            fresh /= np.linalg.norm(fresh, axis=1, keepdims=True).astype(np.float32)
+            qh = np.ascontiguousarray(np.concatenate([rows_np[pick], fresh], 0))
+            ctx.search(qh[:1000], p)
+            t0 = time.perf_counter()
+            offs, out = ctx.search(qh, p)
+            dt = (time.perf_counter() - t0) * 1e3
+            se[f"p={p}"] = {"queries_per_sec": nqe / (dt / 1e3), "ms": dt, "queries": nqe, "candidates": int(len(out)),
+                            "h2d_bytes": int(qh.nbytes), "d2h_bytes": int(offs.nbytes + out.nbytes),
+                            "path": "vi_search_begin + vi_search_fetch, pageable host buffers"}
+            log(f"search e2e p={p}: {dt:.1f} ms for {nqe} queries, {len(out)} candidates")
+        result.setdefault("search", {})["e2e"] = se
     if args.topk > 0:
         # quality layer: k nearest candidates vs exact k-NN
         k, nq_t = args.topk, 2000

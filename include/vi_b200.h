@@ -59,6 +59,8 @@ typedef struct vi_build_info
   int32_t reserved;
   double subtree_ms;     /* fast mode: device time of the sub-tree kernel (ranges of <= 32 points, vi_subtree.cuh) */
   int64_t subtree_ranges;/* ranges handed to it */
+  int32_t shared_retry;  /* multi-rank: 1 if the build was redone with fewer shared levels (a tightly clustered top range) */
+  int32_t reserved2;
 } vi_build_info;
 
 /* Per-level record (profiling / roofline accounting, Program.cs has only a whole-build Stopwatch). */
@@ -136,6 +138,11 @@ int vi_textindex_copy(const vi_ctx* ctx, int64_t* range_id, int16_t* dimension, 
  * and cap < *total (offsets and *total are still valid). */
 int vi_search(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int64_t* offsets,
               int64_t* ids, int64_t cap, int64_t* total);
+/* The same search in two steps that walk the table twice in all (vi_search called twice walks it three times):
+ * begin stages the queries and counts (-> *total), fetch fills and copies offsets[nq+1] and ids[*total] (cap >= *total).
+ * A build, reserve or another begin in between invalidates the pending search (fetch -> VI_ERR_STATE). */
+int vi_search_begin(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int64_t* total);
+int vi_search_fetch(vi_ctx* ctx, int64_t* offsets, int64_t* ids, int64_t cap);
 /* Device-resident form: d_queries, d_offsets[nq+1], d_ids[cap] are device pointers; *total is a host value.
  * visits (host, may be NULL) receives the number of table rows visited. */
 int vi_search_device(vi_ctx* ctx, const float* d_queries, int64_t nq, int32_t dims, float proximity,
@@ -154,17 +161,28 @@ int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims
 int vi_search_topk(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int32_t k, int32_t metric,
                    int64_t* ids, float* dist, int32_t* count, int64_t* candidates);
 
-/* ---- multi-GPU (one process per GPU; the host supplies the collective, e.g. torch.distributed/NCCL) ----------- */
+/* ---- multi-GPU (one process per GPU) ------------------------------------------------------------------------------ */
 /* A multi-rank vi_build (VI_MODE_FAST only: its integer sums are order-independent) treats the points added to the
  * `world` contexts as ONE data set in rank order (rank 0's points first).  Top levels: every rank reduces its local
  * slice of every range and the sums meet in one all-reduce per level; then each range of level L = ceil(log2 world)+1
  * moves to one owner rank (a single all-to-all) and the owners finish their sub-trees without communication.  After
  * the build a context holds the rows of the shared top levels (replicated) plus the rows of the sub-trees it owns;
- * the union over ranks is the single-rank table.  The two collectives are host callbacks on DEVICE buffers:
+ * the union over ranks is the single-rank table.  A top range too tightly clustered for the integer statistics makes
+ * the build start over with fewer shared levels (vi_build_info.shared_retry), down to handing everything to one rank.
+ *
+ * The library owns the collectives: NCCL (libnccl.so.2, bound at run time) on the context's own stream, so the shared
+ * levels are enqueued without host synchronisation.  Rank 0 calls vi_comm_unique_id, the host passes the 128 bytes to
+ * every rank by whatever means it has, every rank calls vi_comm_init (collective).  world == 1 leaves multi-rank mode. */
+int vi_comm_unique_id(void* out, int32_t bytes /* >= 128 */);
+int vi_comm_init(vi_ctx* ctx, const void* unique_id, int32_t bytes, int32_t rank, int32_t world);
+/* calls / bytes sent so far by [all-reduce, all-to-all, all-gather] (either array may be NULL) */
+int vi_comm_stats(const vi_ctx* ctx, int64_t* calls3, int64_t* bytes3);
+/* Alternative for hosts that bring their own transport: the two collectives as host callbacks on DEVICE buffers
+ * (they must have completed when they return; the library synchronises its stream before calling them):
  *   allreduce: sum of `count` uint64 words, in place, over all ranks;
  *   alltoallv: rank r's send_bytes[d] bytes (consecutive in d_send) go to rank d, which receives recv_bytes[r]
  *              bytes from rank r (consecutive in d_recv, ordered by source rank).
- * Both return 0 on success and must have completed (stream-synchronised) when they return. */
+ * Both return 0 on success. */
 typedef int (*vi_allreduce_u64_fn)(void* user, void* d_buf, int64_t count);
 typedef int (*vi_alltoallv_fn)(void* user, const void* d_send, const int64_t* send_bytes, void* d_recv,
                                const int64_t* recv_bytes);
@@ -176,7 +194,7 @@ int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64
 int vi_shared_rows(const vi_ctx* ctx, int64_t* shared_rows);
 /* After a multi-rank build: gathers every rank's rows so that each context holds the WHOLE range table (row links
  * remapped) and can answer any query -- "search shards the query batch against a replicated range table".  One
- * all-reduce of 32 bytes per row.  Collective: every rank must call it.  The vectors stay with their owners, so
+ * all-gather of 32 bytes per row (plus a sum-all-reduce over the few shared rows).  Collective: every rank must call it.  The vectors stay with their owners, so
  * vi_search_verify is not available on a replicated table. */
 int vi_table_replicate(vi_ctx* ctx);
 

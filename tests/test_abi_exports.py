@@ -48,4 +48,11 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 # comments may cite the oracle as the CPU statement of a rule; code must not load, link or include it
                 assert "import oracle" not in src and "from oracle" not in src and "libvi_oracle" not in src, f
-                assert '#include "vi_oracle' not in src and "dlopen" not in src, f
+                assert '#include "vi_oracle' not in src, f
+                if f == "vi_comm.cu":
+                    # the one place that loads a library at run time: NCCL, and nothing else
+                    import re
+                    names = re.findall(r'"([^"]*\.so[^"]*)"', src)
+                    assert names and all("nccl" in n for n in names), names
+                else:
+                    assert "dlopen" not in src, f

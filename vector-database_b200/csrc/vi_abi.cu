@@ -76,6 +76,9 @@ void vi_destroy(vi_ctx* ctx)
   cudaFree(ctx->q_buf); cudaFree(ctx->off_buf); cudaFree(ctx->ids_buf); cudaFree(ctx->off2_buf);
   cudaFree(ctx->ids2_buf); cudaFree(ctx->search_src); cudaFree(ctx->verify_keep);
   cudaFree(ctx->own_rows); cudaFree(ctx->own_ids); cudaFree(ctx->send_rows); cudaFree(ctx->send_ids);
+  vi_comm_release(ctx);
+  cudaFree(ctx->sh_dev);
+  if (ctx->sh_host) cudaFreeHost(ctx->sh_host);
   cudaFree(ctx->counters);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -226,6 +229,7 @@ int vi_build(vi_ctx* ctx, int32_t mode, vi_build_info* info)
   if (ctx->world > 1 && mode != VI_MODE_FAST)
     return ctx->fail(VI_ERR_INVALID_ARG, "multi-rank build needs VI_MODE_FAST (order-independent sums)");
   VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->pending_nq = -1;
   int rc = vi_build_impl(ctx, mode);
   if (info) *info = ctx->info;
   return rc;
@@ -275,6 +279,7 @@ int vi_ranges_load(vi_ctx* ctx, const int64_t* range_id, const int32_t* dimensio
     ctx->dims = dims;
     ctx->ld = (dims + 3) & ~3;
   }
+  ctx->pending_nq = -1;
   return vi_ranges_load_impl(ctx, range_id, dimension, mid, id, n);
 }
 
@@ -336,6 +341,7 @@ int vi_search_device(vi_ctx* ctx, const float* d_queries, int64_t nq, int32_t di
 
 static int stage_queries(vi_ctx* ctx, const float* queries, int64_t nq)
 {
+  ctx->pending_nq = -1;  // the staged queries / offsets of a vi_search_begin are overwritten
   int rc = grow(ctx, &ctx->q_buf, &ctx->q_cap, nq * ctx->dims + 4);
   if (rc != VI_OK) return rc;
   rc = grow(ctx, &ctx->off_buf, &ctx->off_cap, nq + 2);
@@ -380,6 +386,53 @@ int vi_search(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float
     }
   }
   ctx->search_src = keep_src;
+  return rc;
+}
+
+// Two-step form of vi_search that walks the table only twice in all: begin = count pass (the staged queries and the
+// scanned offsets stay in the context), fetch = fill pass + copies.
+int vi_search_begin(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int64_t* total)
+{
+  if (!ctx || !total) return VI_ERR_INVALID_ARG;
+  ctx->pending_nq = -1;
+  { const int rs = searchable(ctx); if (rs != VI_OK) return rs; }
+  if (dims != ctx->dims) return ctx->fail(VI_ERR_INVALID_ARG, "Invalid vector size.");
+  if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !queries)) return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  int rc = stage_queries(ctx, queries, nq);
+  if (rc != VI_OK) return rc;
+  int* keep_src = ctx->search_src;
+  ctx->search_src = nullptr;
+  rc = vi_search_impl(ctx, ctx->q_buf, nq, proximity, ctx->off_buf, nullptr, 0, total, nullptr, false);
+  ctx->search_src = keep_src;
+  if (rc != VI_OK) return rc;
+  ctx->pending_nq = nq;
+  ctx->pending_total = *total;
+  ctx->pending_prox = proximity;
+  return VI_OK;
+}
+
+int vi_search_fetch(vi_ctx* ctx, int64_t* offsets, int64_t* ids, int64_t cap)
+{
+  if (!ctx || !offsets) return VI_ERR_INVALID_ARG;
+  if (ctx->pending_nq < 0 || !ctx->built) return ctx->fail(VI_ERR_STATE, "vi_search_fetch without vi_search_begin");
+  const int64_t nq = ctx->pending_nq, total = ctx->pending_total;
+  if (total > 0 && (!ids || cap < total)) return ctx->fail(VI_ERR_CAPACITY, "ids capacity smaller than the number of candidates");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  VI_CUDA_TRY(cudaMemcpyAsync(offsets, ctx->off_buf, (size_t)(nq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = VI_OK;
+  if (total > 0)
+  {
+    rc = grow(ctx, &ctx->ids_buf, &ctx->ids_cap, total);
+    int* keep_src = ctx->search_src;
+    ctx->search_src = nullptr;
+    int64_t t2 = 0;
+    if (rc == VI_OK) rc = vi_search_impl(ctx, ctx->q_buf, nq, ctx->pending_prox, ctx->off_buf, ctx->ids_buf, total, &t2, nullptr, true);
+    ctx->search_src = keep_src;
+    if (rc == VI_OK) VI_CUDA_TRY(cudaMemcpyAsync(ids, ctx->ids_buf, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->pending_nq = -1;
   return rc;
 }
 
@@ -446,8 +499,9 @@ int vi_set_collective(vi_ctx* ctx, int32_t rank, int32_t world, vi_allreduce_u64
                       vi_alltoallv_fn alltoallv, void* user)
 {
   if (!ctx) return VI_ERR_INVALID_ARG;
-  if (world < 1 || world > 64 || rank < 0 || rank >= world || (world > 1 && (!allreduce || !alltoallv)))
+  if (world < 1 || world > 64 || rank < 0 || rank >= world || (world > 1 && (!allreduce || !alltoallv)))  // (2^L <= VI_SH_MAXR)
     return ctx->fail(VI_ERR_INVALID_ARG, "bad collective");
+  vi_comm_release(ctx);  // the host's transport replaces a library-owned communicator
   ctx->rank = rank;
   ctx->world = world;
   ctx->allreduce = allreduce;

@@ -926,39 +926,61 @@ static int build_single(vi_ctx* ctx, BuildEnv& env)
 }
 
 // =============================================================================================================
-// multi-rank build (protocol: include/vi_b200.h vi_set_collective, DESIGN.md "Multi-GPU build")
+// multi-rank build (protocol: include/vi_b200.h vi_comm_init / vi_set_collective, DESIGN.md "Multi-GPU build")
 // =============================================================================================================
-struct HostSeg
+constexpr size_t VI_SH_STAGE = 512 * 1024;  // small host-built tables of the ownership phase, one upload
+
+struct ShDev  // device scratch of the shared phase
 {
-  u32 start, lcount;  // local slice
-  u64 gcount;         // points over all ranks
-  i64 rid;
-  u32 row;
+  ShLevel lvl[2];
+  u64 cnt_loc[2 * VI_SH_MAXR];
+  u64 cnt_glb[2 * VI_SH_MAXR];
+  u32 sc[6][VI_SH_MAXR];
+  u64 leaf_ids[VI_SH_MAXROWS];
+  u64 v0[2 * 64];                    // sizes and max|x| of every rank
+  u32 lc_all[64 * VI_SH_MAXR];       // all-gathered local sizes of the last shared level's ranges
+  u32 stat_err;
+  u32 pad[3];
+  unsigned char tables[VI_SH_STAGE];
 };
 
-template <typename T>
-static int upload(vi_ctx* ctx, T* dst, const std::vector<T>& src)
+struct ShHost  // pinned
 {
-  if (src.empty()) return VI_OK;
-  VI_CUDA_TRY(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-  VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // src is a stack/heap temporary
-  return VI_OK;
+  ShLevel fin;
+  u64 v0[2 * 64];
+  u32 lc_all[64 * VI_SH_MAXR];
+  unsigned char tables[VI_SH_STAGE];
+};
+
+__global__ void k_sh_pack0(const float* __restrict__ d_absmax, u32 nloc, int me, int G, u64* __restrict__ v0)
+{
+  const int i = threadIdx.x;
+  if (i < 2 * G) v0[i] = 0;
+  __syncthreads();
+  if (i == 0)
+  {
+    v0[me] = nloc;
+    v0[G + me] = (u64)__float_as_uint(*d_absmax);  // non-negative floats order like their bit patterns
+  }
 }
 
-// all-reduce (sum) of a small host vector of u64 through the device scratch `gacc`
-static int allreduce_host(vi_ctx* ctx, std::vector<u64>& v)
+// a host blob of small tables that becomes one pinned -> device copy
+struct Blob
 {
-  if (v.empty()) return VI_OK;
-  VI_CUDA_TRY(cudaMemcpyAsync(ctx->gacc, v.data(), v.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (ctx->allreduce(ctx->coll_user, ctx->gacc, (int64_t)v.size()) != 0)
-    return ctx->fail(VI_ERR_CUDA, "all-reduce callback failed");
-  VI_CUDA_TRY(cudaMemcpyAsync(v.data(), ctx->gacc, v.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  VI_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  return VI_OK;
-}
+  std::vector<unsigned char> bytes;
+  template <typename T>
+  size_t add(const std::vector<T>& v)
+  {
+    const size_t off = (bytes.size() + 15) & ~(size_t)15;
+    bytes.resize(off + v.size() * sizeof(T) + 16);
+    if (!v.empty()) memcpy(bytes.data() + off, v.data(), v.size() * sizeof(T));
+    return off;
+  }
+};
 
-static int build_sharded(vi_ctx* ctx, BuildEnv& env)
+constexpr int VI_RETRY = -1000;  // internal: rebuild with fewer shared levels
+
+static int build_sharded_try(vi_ctx* ctx, BuildEnv& env, int Lcap, int* retry_level)
 {
   cudaStream_t st = ctx->stream;
   const int G = ctx->world, me = ctx->rank;
@@ -966,223 +988,138 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
   const u32 nloc = (u32)ctx->n;
   cudaEvent_t ev_begin = env_event(ctx, env);
 
-  // ---- global size and quantisation exponent ----------------------------------------------------------------
   // 25 % slack: the points a rank owns after the exchange are rarely exactly its shard size
   int rc = alloc_workspace(ctx, std::max<int64_t>(ctx->n + ctx->n / 4, 4096));
   if (rc != VI_OK) return rc;
-  float amax = 0.f;
-  rc = local_absmax(ctx, ctx->rows, ctx->n, env, &amax);
-  if (rc != VI_OK) return rc;
-  std::vector<u64> v0((size_t)2 * G, 0);
-  v0[me] = nloc;
-  u32 amax_mine = 0;
-  memcpy(&amax_mine, &amax, 4);
-  v0[G + me] = amax_mine;  // non-negative floats order like their bit patterns
-  rc = allreduce_host(ctx, v0);
-  if (rc != VI_OK) return rc;
+  if (!ctx->sh_dev)
+  {
+    VI_CUDA_TRY(cudaMalloc(&ctx->sh_dev, sizeof(ShDev)));
+    VI_CUDA_TRY(cudaMallocHost(&ctx->sh_host, sizeof(ShHost)));
+  }
+  ShDev* sd = (ShDev*)ctx->sh_dev;
+  ShHost* shh = (ShHost*)ctx->sh_host;
+
+  // ---- global size and quantisation exponent: one small all-reduce, the phase's first host synchronisation -----------
+  VI_CUDA_TRY(cudaMemsetAsync(ctx->d_absmax, 0, 4, st));
+  if (nloc > 0)
+  {
+    k_absmax<<<VI_NUM_SMS * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->rows), (size_t)nloc * ld / 4,
+                                             (u32*)ctx->d_absmax);
+    ++env.launches;
+  }
+  k_sh_pack0<<<1, 128, 0, st>>>(ctx->d_absmax, nloc, me, G, sd->v0);
+  ++env.launches;
+  if ((rc = vi_coll_allreduce_u64(ctx, sd->v0, 2 * G))) return rc;
+  VI_CUDA_TRY(cudaMemcpyAsync(shh->v0, sd->v0, (size_t)2 * G * 8, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaStreamSynchronize(st));
   u64 nglobal = 0;
   u32 amax_bits = 0;
   for (int g = 0; g < G; ++g)
   {
-    nglobal += v0[g];
-    amax_bits = std::max(amax_bits, (u32)v0[G + g]);
+    nglobal += shh->v0[g];
+    amax_bits = std::max(amax_bits, (u32)shh->v0[G + g]);
   }
+  float amax = 0.f;
   memcpy(&amax, &amax_bits, 4);
   set_q_exponent(ctx, env, amax);
   if (nglobal >= 0x7fffffffull) return ctx->fail(VI_ERR_CAPACITY, "more than 2^31-2 points");
   if (nglobal == 0) return finish_table(ctx, env, 0, ev_begin, nullptr);
 
-  // ---- phase A: shared levels -------------------------------------------------------------------------------
+  // ---- phase A: shared levels, enqueued without a host synchronisation ------------------------------------------------
   int L = 1;
   while ((1 << (L - 1)) < G) ++L;  // L = ceil(log2 G) + 1: about 2G ranges to balance over G owners
-  std::vector<HostSeg> segs{{0u, nloc, nglobal, 0, 0u}};
-  // shared rows are assembled on the host (a few dozen rows) and uploaded at the end of the phase
-  std::vector<i64> h_rid{0};
-  std::vector<int> h_low{-1}, h_high{-1}, h_leaf{nglobal == 1 ? 1 : 0};
-  u32 T = 1;  // shared rows so far
-  int cur = 0;
-  int level = 0;
+  L = std::min(L, Lcap);
   if (nloc > 0)
   {
     k_init_level0<<<(nloc + 255) / 256, 256, 0, st>>>(ctx->perm[0], ctx->pid[0], ctx->ids, ctx->seg_of[0], nloc,
                                                       ctx->seg[0], ctx->big_list[0], ctx->t_rid, ctx->t_low, ctx->t_high);
     ++env.launches;
   }
-  // scratch (the level loop's per-range prefix array is unused until phase C): ids of shared leaf rows (the holder
-  // writes), then the small host-built tables of this phase
-  u64* leaf_ids = reinterpret_cast<u64*>(ctx->c_pre);
-  u32* scratch32 = reinterpret_cast<u32*>(ctx->c_pre) + 16384;
-  VI_CUDA_TRY(cudaMemsetAsync(leaf_ids, 0, 4096 * sizeof(u64), st));
   VI_CUDA_TRY(cudaMemsetAsync(ctx->lv, 0, sizeof(LevelDev) * VI_LV_N, st));
-  if (nglobal == 1)
-  {
-    if (nloc == 1)
-      VI_CUDA_TRY(cudaMemcpyAsync(leaf_ids, ctx->ids, 8, cudaMemcpyDeviceToDevice, st));
-    segs.clear();
-  }
+  VI_CUDA_TRY(cudaMemsetAsync(sd->leaf_ids, 0, sizeof(sd->leaf_ids), st));
+  VI_CUDA_TRY(cudaMemsetAsync(&sd->stat_err, 0, 16, st));
+  TableOut tout{ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high};
   StatsOut sout{ctx->t_dim, ctx->t_mid, ctx->t_id};
-  u32* lvl_counters = ctx->counters + 16;
+  k_sh_begin<<<1, 1, 0, st>>>(&sd->lvl[0], ctx->lv, nloc, nglobal, ctx->chunk_first[0], ctx->seg[0], ctx->big_list[0], tout);
+  ++env.launches;
+  if (nglobal == 1 && nloc == 1) VI_CUDA_TRY(cudaMemcpyAsync(sd->leaf_ids, ctx->ids, 8, cudaMemcpyDeviceToDevice, st));
   const FlagScan fs{ctx->fbits, ctx->wloc, ctx->ftile};
-
-  for (; level < L && !segs.empty(); ++level)
+  ShScatter sc{sd->sc[0], sd->sc[1], sd->sc[2], sd->sc[3], (int*)sd->sc[4], (int*)sd->sc[5]};
+  std::vector<LevelEvents> evs;
+  int level = 0;
+  for (; level < L; ++level)
   {
     if (level >= VI_MAX_DEPTH) return ctx->fail(VI_ERR_OVERFLOW, "rangeId overflow (IndexBuilder.cs:99)");
-    const int nxt = cur ^ 1;
+    const int cur = level & 1, nxt = cur ^ 1;
     const int mx = (level & 1) == 0;
-    const u32 R = (u32)segs.size();
-    const u32 T_before = T;
+    const u32 Rb = (u32)std::min(1 << level, VI_SH_MAXR);  // bound on the level's ranges
     SegLevel& sg = ctx->seg[cur];
-    cudaEvent_t e0 = env_event(ctx, env);
-    // range list of this level (identical on every rank except for the local slices)
-    std::vector<u32> h_start(R), h_count(R), h_row(R), h_big(R), h_cf(R + 1);
-    std::vector<i64> h_srid(R);
-    u32 A = 0, chunks = 0;
-    for (u32 i = 0; i < R; ++i)
-    {
-      h_start[i] = segs[i].start;
-      h_count[i] = segs[i].lcount;
-      h_row[i] = segs[i].row;
-      h_srid[i] = segs[i].rid;
-      h_big[i] = i;
-      h_cf[i] = chunks;
-      chunks += (segs[i].lcount + VI_CHUNK - 1) / VI_CHUNK;
-      A += segs[i].lcount;
-    }
-    h_cf[R] = chunks;
-    LevelDev hl{};
-    hl.A = A;
-    hl.R = R;
-    hl.nbig = R;
-    hl.chunks = chunks;
-    std::vector<LevelDev> h_lvrec{hl};
     LevelDev* lvp = ctx->lv + level;
-    if ((rc = upload(ctx, sg.start, h_start)) || (rc = upload(ctx, sg.count, h_count)) || (rc = upload(ctx, sg.row, h_row)) ||
-        (rc = upload(ctx, sg.rid, h_srid)) || (rc = upload(ctx, ctx->big_list[cur], h_big)) ||
-        (rc = upload(ctx, ctx->chunk_first[cur], h_cf)) || (rc = upload(ctx, lvp, h_lvrec)))
-      return rc;
+    LevelEvents ev;
+    ev.e0 = env_event(ctx, env);
     // local sums of every range -> gacc, one all-reduce, identical split on every rank
-    VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)R * env.gstride * sizeof(u64), st));
-    if (chunks > 0) launch_big_fast(ctx, env, lvp, ctx->rows, cur, chunks, mx, 0, ctx->gacc, 0xffffffffu, nullptr);
-    VI_CUDA_TRY(cudaStreamSynchronize(st));
-    if (ctx->allreduce(ctx->coll_user, ctx->gacc, (int64_t)((size_t)R * env.gstride)) != 0)
-      return ctx->fail(VI_ERR_CUDA, "all-reduce callback failed");
-    VI_CUDA_TRY(cudaMemsetAsync(lvl_counters, 0, 32, st));
-    k_finalize_big_fast<<<(R * 32 + 255) / 256, 256, 0, st>>>(lvp, sg, ctx->big_list[cur], ctx->gacc, nullptr, ld, dims,
-                                                              env.qinv, mx, sout, ctx->rows, ctx->perm[cur], 0, 1,
-                                                              lvl_counters + 1, nullptr, nullptr);
-    ++env.launches;
-    cudaEvent_t e1 = env_event(ctx, env);
-    // local partition flags and child sizes
-    std::vector<u32> h_nlo(R, 0);
-    if (A > 0)
-    {
-      k_flags<<<A / FL_TILE + 1, 256, 0, st>>>(lvp, &lvp->ticket[0], sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur],
-                                               ctx->rows, ld, ctx->fbits, ctx->wloc, ctx->ftile);
-      k_seg_nlo<<<(R + 255) / 256, 256, 0, st>>>(sg, R, fs, ctx->seg_nlo, ctx->seg_hbase);
-      env.launches += 2;
-      VI_CUDA_TRY(cudaMemcpyAsync(h_nlo.data(), ctx->seg_nlo, R * 4, cudaMemcpyDeviceToHost, st));
-    }
-    u32 errflag = 0;
-    VI_CUDA_TRY(cudaMemcpyAsync(&errflag, lvl_counters + 1, 4, cudaMemcpyDeviceToHost, st));
-    VI_CUDA_TRY(cudaStreamSynchronize(st));
-    if (errflag)
-      return ctx->fail(VI_ERR_STATE, "multi-rank build: a range of the shared top levels is too tightly clustered for the "
-                                     "fixed-point statistics (its float32 fallback needs all rows on one rank)");
-    std::vector<u64> cnt((size_t)2 * R);
-    for (u32 i = 0; i < R; ++i)
-    {
-      const u32 llo = segs[i].lcount ? h_nlo[i] : 0u;
-      cnt[2 * i] = llo;
-      cnt[2 * i + 1] = segs[i].lcount - llo;
-    }
-    std::vector<u64> gcnt = cnt;
-    if ((rc = allreduce_host(ctx, gcnt))) return rc;
-    // children: rows, leaves, next-level ranges, local destinations (same order as the single-rank builder:
-    // by range, low child before high child)
-    std::vector<HostSeg> next;
-    std::vector<u32> lo_dst(R, VI_NONE), hi_dst(R, VI_NONE), lo_seg(R, 0), hi_seg(R, 0);
-    std::vector<int> lo_leaf(R, -1), hi_leaf(R, -1);
-    u32 npos = 0;
-    for (u32 i = 0; i < R; ++i)
-    {
-      for (int side = 0; side < 2; ++side)
-      {
-        const u64 g = gcnt[2 * i + side];
-        const u32 l = (u32)cnt[2 * i + side];
-        if (g == 0) continue;  // empty range: no row (IndexBuilder.cs:70-73)
-        const u32 row = T++;
-        h_rid.push_back(segs[i].rid * 2 + 1 + side);
-        h_low.push_back(-1);
-        h_high.push_back(-1);
-        h_leaf.push_back(g == 1 ? 1 : 0);
-        (side ? h_high : h_low)[segs[i].row] = (int)row;
-        if (g == 1)
-          (side ? hi_leaf : lo_leaf)[i] = (int)row;
-        else
-        {
-          (side ? hi_dst : lo_dst)[i] = npos;
-          (side ? hi_seg : lo_seg)[i] = (u32)next.size();
-          next.push_back({npos, l, g, segs[i].rid * 2 + 1 + side, row});
-          npos += l;
-        }
-      }
-    }
-    if (T >= 4096) return ctx->fail(VI_ERR_CAPACITY, "too many shared rows");
-    if (A > 0)
-    {
-      u32* d = scratch32;  // the six per-range arrays
-      if ((rc = upload(ctx, d, lo_dst)) || (rc = upload(ctx, d + R, hi_dst)) || (rc = upload(ctx, d + 2 * R, lo_seg)) ||
-          (rc = upload(ctx, d + 3 * R, hi_seg)) || (rc = upload(ctx, (int*)(d + 4 * R), lo_leaf)) ||
-          (rc = upload(ctx, (int*)(d + 5 * R), hi_leaf)))
-        return rc;
-      ShScatter sc{d, d + R, d + 2 * R, d + 3 * R, (const int*)(d + 4 * R), (const int*)(d + 5 * R)};
-      k_scatter_shared<<<(A + 255) / 256, 256, 0, st>>>(sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], A, fs,
-                                                        ctx->seg_hbase, sc, ctx->perm[nxt], ctx->pid[nxt],
-                                                        ctx->seg_of[nxt], leaf_ids, ctx->t_src);
-      ++env.launches;
-    }
-    cudaEvent_t e2 = env_event(ctx, env);
-    VI_CUDA_TRY(cudaStreamSynchronize(st));
+    VI_CUDA_TRY(cudaMemsetAsync(ctx->gacc, 0, (size_t)Rb * env.gstride * sizeof(u64), st));
+    launch_big_fast(ctx, env, lvp, ctx->rows, cur, nloc / VI_CHUNK + Rb + 1, mx, 0, ctx->gacc, 0xffffffffu, nullptr);
+    if ((rc = vi_coll_allreduce_u64(ctx, ctx->gacc, (int64_t)((size_t)Rb * env.gstride)))) return rc;
+    k_finalize_big_fast<<<(Rb * 32 + 255) / 256, 256, 0, st>>>(lvp, sg, ctx->big_list[cur], ctx->gacc, nullptr, ld, dims,
+                                                               env.qinv, mx, sout, ctx->rows, ctx->perm[cur], 0, 1,
+                                                               &sd->stat_err, nullptr, nullptr);
+    ev.e1 = env_event(ctx, env);
+    // local partition flags and child sizes; global child sizes; children (identical on every rank); local scatter
+    k_flags<<<nloc / FL_TILE + 1, 256, 0, st>>>(lvp, &lvp->ticket[0], sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur],
+                                                ctx->rows, ld, ctx->fbits, ctx->wloc, ctx->ftile);
+    k_seg_nlo<<<(Rb + 255) / 256, 256, 0, st>>>(lvp, sg, fs, ctx->seg_nlo, ctx->seg_hbase);
+    k_sh_counts<<<(Rb + 255) / 256, 256, 0, st>>>(&sd->lvl[cur], ctx->seg_nlo, Rb, sd->cnt_loc, sd->cnt_glb);
+    if ((rc = vi_coll_allreduce_u64(ctx, sd->cnt_glb, 2 * (int64_t)Rb))) return rc;
+    k_sh_next<<<1, 1, 0, st>>>(&sd->lvl[cur], &sd->lvl[nxt], sd->cnt_loc, sd->cnt_glb, (u32)level, &sd->stat_err, sc,
+                               ctx->seg[nxt], ctx->big_list[nxt], ctx->chunk_first[nxt], lvp + 1, tout);
+    k_scatter_shared<<<nloc / 256 + 1, 256, 0, st>>>(lvp, sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], fs,
+                                                         ctx->seg_hbase, sc, ctx->perm[nxt], ctx->pid[nxt], ctx->seg_of[nxt],
+                                                         sd->leaf_ids, ctx->t_src);
+    env.launches += 6;
+    ev.e2 = env_event(ctx, env);
+    evs.push_back(ev);
+  }
+  const int cur = level & 1;  // buffers of the ranges of level L
+  ShLevel* fin_d = &sd->lvl[cur];
+  if ((rc = vi_coll_allreduce_u64(ctx, sd->leaf_ids, VI_SH_MAXROWS))) return rc;
+  k_sh_leaf_ids<<<(VI_SH_MAXROWS + 255) / 256, 256, 0, st>>>(fin_d, sd->leaf_ids, ctx->t_dim, ctx->t_id);
+  ++env.launches;
+  if ((rc = vi_coll_allgather(ctx, fin_d->lcount, sd->lc_all, (int64_t)VI_SH_MAXR * 4))) return rc;
+  VI_CUDA_TRY(cudaMemcpyAsync(&shh->fin, fin_d, sizeof(ShLevel), cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaMemcpyAsync(shh->lc_all, sd->lc_all, (size_t)G * VI_SH_MAXR * 4, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaMemcpyAsync(ctx->h_lv, ctx->lv, sizeof(LevelDev) * (size_t)(level + 1), cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaStreamSynchronize(st));  // the phase's second host synchronisation
+  VI_CUDA_TRY(cudaGetLastError());
+  const ShLevel& fin = shh->fin;
+  if (fin.err_level != VI_NONE)
+  {
+    // a range of the shared levels is too tightly clustered for the integer statistics: its float32 fallback needs all
+    // its rows on one rank in global order, so the ranges are handed to their owners one level earlier
+    *retry_level = (int)fin.err_level;
+    return VI_RETRY;
+  }
+  for (int l = 0; l < level; ++l)
+  {
+    if (ctx->h_lv[l].R == 0) continue;
     vi_level_info li{};
-    li.level = level;
-    li.ranges = R;
-    li.points = A;  // local points visited
-    li.rows_emitted = (int64_t)T - (int64_t)T_before;
+    li.level = l;
+    li.ranges = ctx->h_lv[l].R;
+    li.points = ctx->h_lv[l].A;  // local points visited
+    li.rows_emitted = ctx->h_lv[l + 1].rows;
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventElapsedTime(&ms, evs[l].e0, evs[l].e1);
     li.stats_ms = ms;
-    cudaEventElapsedTime(&ms, e1, e2);
+    cudaEventElapsedTime(&ms, evs[l].e1, evs[l].e2);
     li.partition_ms = ms;
     ctx->levels.push_back(li);
-    ctx->info.point_visits += A;
-    segs.swap(next);
-    cur = nxt;
+    ctx->info.point_visits += li.points;
   }
-
-  // shared rows: host-assembled columns + leaf ids (owner wrote, everyone sums)
-  {
-    std::vector<u64> lid(T, 0);
-    VI_CUDA_TRY(cudaMemcpyAsync(lid.data(), leaf_ids, T * 8, cudaMemcpyDeviceToHost, st));
-    VI_CUDA_TRY(cudaStreamSynchronize(st));
-    if ((rc = allreduce_host(ctx, lid))) return rc;
-    if ((rc = upload(ctx, ctx->t_rid, h_rid)) || (rc = upload(ctx, ctx->t_low, h_low)) || (rc = upload(ctx, ctx->t_high, h_high)))
-      return rc;
-    for (u32 r = 0; r < T; ++r)
-      if (h_leaf[r])
-      {
-        const int dimv = -1;
-        const float midv = 0.f;
-        const i64 idv = (i64)lid[r];
-        VI_CUDA_TRY(cudaMemcpyAsync(ctx->t_dim + r, &dimv, 4, cudaMemcpyHostToDevice, st));
-        VI_CUDA_TRY(cudaMemcpyAsync(ctx->t_mid + r, &midv, 4, cudaMemcpyHostToDevice, st));
-        VI_CUDA_TRY(cudaMemcpyAsync(ctx->t_id + r, &idv, 8, cudaMemcpyHostToDevice, st));
-        VI_CUDA_TRY(cudaStreamSynchronize(st));
-      }
-  }
+  const u32 T = fin.T;
   ctx->shared_rows = T;
 
-  // ---- phase B: ownership exchange --------------------------------------------------------------------------
-  const u32 RL = (u32)segs.size();
+  // ---- phase B: ownership exchange --------------------------------------------------------------------------------------
+  const u32 RL = fin.R;
   ctx->own_n = 0;
   LevelState s{};
   s.row_next = T;
@@ -1191,13 +1128,11 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
   if (RL > 0)
   {
     // who holds how much of each range
-    std::vector<u64> mat((size_t)G * RL, 0);
-    for (u32 i = 0; i < RL; ++i) mat[(size_t)me * RL + i] = segs[i].lcount;
-    if ((rc = allreduce_host(ctx, mat))) return rc;
+    auto held = [&](int g, u32 i) -> u64 { return shh->lc_all[(size_t)g * VI_SH_MAXR + i]; };
     // owners: largest range first to the least loaded rank (ties: lower range index, lower rank)
     std::vector<u32> order(RL), owner(RL);
     for (u32 i = 0; i < RL; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return segs[a].gcount > segs[b].gcount; });
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return fin.gcount[a] > fin.gcount[b]; });
     std::vector<u64> load(G, 0);
     for (u32 i : order)
     {
@@ -1205,36 +1140,86 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
       for (int g = 1; g < G; ++g)
         if (load[g] < load[best]) best = g;
       owner[i] = (u32)best;
-      load[best] += segs[i].gcount;
+      load[best] += fin.gcount[i];
     }
-    // root rows of ranges owned elsewhere are placeholders here: Dimension -2
-    for (u32 i = 0; i < RL; ++i)
-      if (owner[i] != (u32)me)
-      {
-        const int dimv = -2;
-        VI_CUDA_TRY(cudaMemcpyAsync(ctx->t_dim + segs[i].row, &dimv, 4, cudaMemcpyHostToDevice, st));
-        VI_CUDA_TRY(cudaStreamSynchronize(st));
-      }
     // send layout: by destination rank, then range index, then local position
-    std::vector<u32> send_base(RL, 0);
+    std::vector<u32> send_base(RL, 0), placeholders;
     std::vector<int64_t> send_rows_n(G, 0), recv_rows_n(G, 0);
-    u32 off = 0;
+    u32 off = 0, A = 0;
     for (int d = 0; d < G; ++d)
       for (u32 i = 0; i < RL; ++i)
         if (owner[i] == (u32)d)
         {
           send_base[i] = off;
-          off += segs[i].lcount;
-          send_rows_n[d] += segs[i].lcount;
+          off += fin.lcount[i];
+          send_rows_n[d] += fin.lcount[i];
         }
     u64 nown = 0;
+    for (u32 i = 0; i < RL; ++i)
+    {
+      A += fin.lcount[i];
+      if (owner[i] != (u32)me) placeholders.push_back(fin.row[i]);  // root rows of ranges owned elsewhere: Dimension -2
+    }
     for (int g = 0; g < G; ++g)
       for (u32 i = 0; i < RL; ++i)
         if (owner[i] == (u32)me)
         {
-          recv_rows_n[g] += (int64_t)mat[(size_t)g * RL + i];
-          nown += mat[(size_t)g * RL + i];
+          recv_rows_n[g] += (int64_t)held(g, i);
+          nown += held(g, i);
         }
+    // forest of owned ranges, pieces in source-rank order (= global stable order)
+    std::vector<u32> piece_dst, piece_src, piece_seg, f_start, f_count, f_row, f_big, f_cf;
+    std::vector<i64> f_rid;
+    std::vector<u32> src_off(G, 0);  // running offset inside each source's block of the receive buffer
+    {
+      u32 acc = 0;
+      for (int g = 0; g < G; ++g) { src_off[g] = acc; acc += (u32)recv_rows_n[g]; }
+    }
+    u32 pos = 0, minseg = 0xffffffffu, maxseg = 0, chunks = 0;
+    for (u32 i = 0; i < RL; ++i)
+    {
+      if (owner[i] != (u32)me) continue;
+      const u32 fsi = (u32)f_start.size();
+      f_start.push_back(pos);
+      f_count.push_back((u32)fin.gcount[i]);
+      f_rid.push_back(fin.rid[i]);
+      f_row.push_back(fin.row[i]);
+      for (int g = 0; g < G; ++g)
+      {
+        const u32 len = (u32)held(g, i);
+        if (len == 0) continue;
+        piece_dst.push_back(pos);
+        piece_src.push_back(src_off[g]);
+        piece_seg.push_back(fsi);
+        pos += len;
+        src_off[g] += len;
+      }
+      const u32 c = (u32)fin.gcount[i];
+      minseg = std::min(minseg, c);
+      maxseg = std::max(maxseg, c);
+      if (c >= env.t_big)
+      {
+        f_big.push_back(fsi);
+        f_cf.push_back(chunks);
+        chunks += (c + VI_CHUNK - 1) / VI_CHUNK;
+      }
+    }
+    f_cf.push_back(chunks);
+    // every small table in one upload
+    Blob blob;
+    const size_t o_rid = blob.add(f_rid), o_sb = blob.add(send_base), o_ph = blob.add(placeholders), o_pd = blob.add(piece_dst),
+                 o_ps = blob.add(piece_src), o_pg = blob.add(piece_seg), o_fs = blob.add(f_start), o_fc = blob.add(f_count),
+                 o_fr = blob.add(f_row), o_fb = blob.add(f_big), o_cf = blob.add(f_cf);
+    if (blob.bytes.size() > VI_SH_STAGE) return ctx->fail(VI_ERR_CAPACITY, "ownership tables too large");
+    memcpy(shh->tables, blob.bytes.data(), blob.bytes.size());
+    VI_CUDA_TRY(cudaMemcpyAsync(sd->tables, shh->tables, blob.bytes.size(), cudaMemcpyHostToDevice, st));
+    auto dptr = [&](size_t o) { return sd->tables + o; };
+    if (!placeholders.empty())
+    {
+      k_sh_placeholders<<<((u32)placeholders.size() + 255) / 256, 256, 0, st>>>((const u32*)dptr(o_ph), (u32)placeholders.size(),
+                                                                                ctx->t_dim);
+      ++env.launches;
+    }
     // exchange buffers are kept across builds (cudaMalloc/cudaFree of GB-sized buffers costs milliseconds)
     if ((int64_t)nloc > ctx->send_cap)
     {
@@ -1254,76 +1239,27 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
       VI_CUDA_TRY(cudaMalloc((void**)&ctx->own_ids, c * sizeof(i64)));
       ctx->own_cap = (int64_t)c;
     }
-    float* send_rows = ctx->send_rows;
-    i64* send_ids = ctx->send_ids;
-    u32 A = 0;
-    for (u32 i = 0; i < RL; ++i) A += segs[i].lcount;
     if (A > 0)
     {
-      // seg[cur] of the last shared level still describes local slices: refresh starts/counts for the pack kernel
-      std::vector<u32> h_start(RL), h_count(RL);
-      for (u32 i = 0; i < RL; ++i) { h_start[i] = segs[i].start; h_count[i] = segs[i].lcount; }
-      if ((rc = upload(ctx, ctx->seg[cur].start, h_start)) || (rc = upload(ctx, ctx->seg[cur].count, h_count)) ||
-          (rc = upload(ctx, scratch32, send_base)))
-        return rc;
+      // seg[cur] (written by the last k_sh_next) describes the local slices of the level-L ranges
       const size_t threads = (size_t)A * (ld / 4);
       k_pack_rows<<<(u32)((threads + 255) / 256), 256, 0, st>>>(ctx->seg[cur], ctx->seg_of[cur], ctx->perm[cur],
-                                                                ctx->pid[cur], ctx->rows, ld, A, scratch32, send_rows,
-                                                                send_ids);
+                                                                ctx->pid[cur], ctx->rows, ld, A, (const u32*)dptr(o_sb),
+                                                                ctx->send_rows, ctx->send_ids);
       ++env.launches;
     }
-    VI_CUDA_TRY(cudaStreamSynchronize(st));
     std::vector<int64_t> sb(G), rb(G);
     for (int g = 0; g < G; ++g) { sb[g] = send_rows_n[g] * ld * 4; rb[g] = recv_rows_n[g] * ld * 4; }
-    int cerr = ctx->alltoallv(ctx->coll_user, send_rows, sb.data(), ctx->own_rows, rb.data());
+    if ((rc = vi_coll_alltoallv(ctx, ctx->send_rows, sb.data(), ctx->own_rows, rb.data()))) return rc;
     for (int g = 0; g < G; ++g) { sb[g] = send_rows_n[g] * 8; rb[g] = recv_rows_n[g] * 8; }
-    if (cerr == 0) cerr = ctx->alltoallv(ctx->coll_user, send_ids, sb.data(), ctx->own_ids, rb.data());
-    if (cerr != 0) return ctx->fail(VI_ERR_CUDA, "all-to-all callback failed");
+    if ((rc = vi_coll_alltoallv(ctx, ctx->send_ids, sb.data(), ctx->own_ids, rb.data()))) return rc;
     ctx->own_n = (int64_t)nown;
 
-    // ---- phase C: forest of owned ranges, pieces in source-rank order (= global stable order) --------------
+    // ---- phase C: the owned forest, ordinary level loop ------------------------------------------------------------------
     rc = alloc_workspace(ctx, std::max<int64_t>((int64_t)nown, 1024));
     if (rc != VI_OK) return rc;
     rc = grow_table(ctx, (int64_t)(2 * nown + nown / 8 + 1024 + T), T);
     if (rc != VI_OK) return rc;
-    std::vector<u32> piece_dst, piece_src, piece_seg, f_start, f_count, f_row, f_big;
-    std::vector<i64> f_rid;
-    std::vector<u32> src_off(G, 0);  // running offset inside each source's block of the receive buffer
-    {
-      u32 acc = 0;
-      for (int g = 0; g < G; ++g) { src_off[g] = acc; acc += (u32)recv_rows_n[g]; }
-    }
-    u32 pos = 0, minseg = 0xffffffffu, maxseg = 0, chunks = 0;
-    std::vector<u32> f_cf;
-    for (u32 i = 0; i < RL; ++i)
-    {
-      if (owner[i] != (u32)me) continue;
-      const u32 fs = (u32)f_start.size();
-      f_start.push_back(pos);
-      f_count.push_back((u32)segs[i].gcount);
-      f_rid.push_back(segs[i].rid);
-      f_row.push_back(segs[i].row);
-      for (int g = 0; g < G; ++g)
-      {
-        const u32 len = (u32)mat[(size_t)g * RL + i];
-        if (len == 0) continue;
-        piece_dst.push_back(pos);
-        piece_src.push_back(src_off[g]);
-        piece_seg.push_back(fs);
-        pos += len;
-        src_off[g] += len;
-      }
-      const u32 c = (u32)segs[i].gcount;
-      minseg = std::min(minseg, c);
-      maxseg = std::max(maxseg, c);
-      if (c >= env.t_big)
-      {
-        f_big.push_back(fs);
-        f_cf.push_back(chunks);
-        chunks += (c + VI_CHUNK - 1) / VI_CHUNK;
-      }
-    }
-    f_cf.push_back(chunks);
     s.A = pos;
     s.R = (u32)f_start.size();
     s.nbig = (u32)f_big.size();
@@ -1333,15 +1269,17 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
     if (s.R > 0)
     {
       SegLevel& f = ctx->seg[0];
-      u32* d = scratch32;
+      const size_t r4 = (size_t)s.R * 4;
+      VI_CUDA_TRY(cudaMemcpyAsync(f.start, dptr(o_fs), r4, cudaMemcpyDeviceToDevice, st));
+      VI_CUDA_TRY(cudaMemcpyAsync(f.count, dptr(o_fc), r4, cudaMemcpyDeviceToDevice, st));
+      VI_CUDA_TRY(cudaMemcpyAsync(f.row, dptr(o_fr), r4, cudaMemcpyDeviceToDevice, st));
+      VI_CUDA_TRY(cudaMemcpyAsync(f.rid, dptr(o_rid), (size_t)s.R * 8, cudaMemcpyDeviceToDevice, st));
+      if (s.nbig) VI_CUDA_TRY(cudaMemcpyAsync(ctx->big_list[0], dptr(o_fb), (size_t)s.nbig * 4, cudaMemcpyDeviceToDevice, st));
+      VI_CUDA_TRY(cudaMemcpyAsync(ctx->chunk_first[0], dptr(o_cf), ((size_t)s.nbig + 1) * 4, cudaMemcpyDeviceToDevice, st));
       const u32 np = (u32)piece_dst.size();
-      if ((rc = upload(ctx, f.start, f_start)) || (rc = upload(ctx, f.count, f_count)) || (rc = upload(ctx, f.rid, f_rid)) ||
-          (rc = upload(ctx, f.row, f_row)) || (rc = upload(ctx, ctx->big_list[0], f_big)) ||
-          (rc = upload(ctx, ctx->chunk_first[0], f_cf)) || (rc = upload(ctx, d, piece_dst)) ||
-          (rc = upload(ctx, d + np, piece_src)) || (rc = upload(ctx, d + 2 * np, piece_seg)))
-        return rc;
-      k_forest_init<<<(s.A + 255) / 256, 256, 0, st>>>(s.A, np, d, d + np, d + 2 * np, ctx->own_ids, ctx->perm[0],
-                                                       ctx->pid[0], ctx->seg_of[0]);
+      k_forest_init<<<(s.A + 255) / 256, 256, 0, st>>>(s.A, np, (const u32*)dptr(o_pd), (const u32*)dptr(o_ps),
+                                                       (const u32*)dptr(o_pg), ctx->own_ids, ctx->perm[0], ctx->pid[0],
+                                                       ctx->seg_of[0]);
       ++env.launches;
       rc = run_levels(ctx, env, s, ctx->own_rows);
       if (rc != VI_OK) return rc;
@@ -1350,37 +1288,61 @@ static int build_sharded(vi_ctx* ctx, BuildEnv& env)
   return finish_table(ctx, env, s.row_next, ev_begin, ctx->own_n > 0 ? ctx->own_rows : ctx->rows);
 }
 
-// Replicates the table of a multi-rank build on every rank (for query-sharded search).
+static int build_sharded(vi_ctx* ctx, BuildEnv& env)
+{
+  int Lcap = 64;
+  for (;;)
+  {
+    int retry_level = 0;
+    const int rc = build_sharded_try(ctx, env, Lcap, &retry_level);
+    if (rc != VI_RETRY) return rc;
+    // every rank sees the same err_level (it comes from all-reduced statistics), so every rank retries alike
+    Lcap = retry_level;
+    ctx->levels.clear();
+    ctx->info.point_visits = 0;
+    ctx->info.shared_retry = 1;
+  }
+}
+
+// Replicates the table of a multi-rank build on every rank (for query-sharded search): the rows of the shared levels
+// meet in a small sum-all-reduce (a level-L root row comes from its owner), the owned sub-trees in one all-gather.
 int vi_table_replicate_impl(vi_ctx* ctx)
 {
   if (ctx->world <= 1 || ctx->replicated) return VI_OK;
   cudaStream_t st = ctx->stream;
   const int G = ctx->world, me = ctx->rank;
   const u32 T = (u32)ctx->shared_rows, rows = (u32)ctx->t_rows;
-  std::vector<u64> own((size_t)G, 0);
-  own[me] = rows - T;
-  int rc = allreduce_host(ctx, own);
+  if (!ctx->sh_dev) return ctx->fail(VI_ERR_STATE, "no multi-rank build to replicate");
+  ShDev* sd = (ShDev*)ctx->sh_dev;
+  ShHost* shh = (ShHost*)ctx->sh_host;
+  // how many rows every rank owns
+  const u64 mine = rows - T;
+  VI_CUDA_TRY(cudaMemsetAsync(sd->v0, 0, sizeof(sd->v0), st));
+  VI_CUDA_TRY(cudaMemcpyAsync(sd->v0 + me, &mine, 8, cudaMemcpyHostToDevice, st));
+  int rc = vi_coll_allreduce_u64(ctx, sd->v0, G);
   if (rc != VI_OK) return rc;
+  VI_CUDA_TRY(cudaMemcpyAsync(shh->v0, sd->v0, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaStreamSynchronize(st));
   u64 total = T, my_off = T;
+  std::vector<int64_t> off(G), len(G);
   for (int g = 0; g < G; ++g)
   {
-    if (g < me) my_off += own[g];
-    total += own[g];
+    off[g] = (int64_t)total * 32;
+    len[g] = (int64_t)shh->v0[g] * 32;
+    if (g < me) my_off += shh->v0[g];
+    total += shh->v0[g];
   }
   if (total >= 0x7fffffffull) return ctx->fail(VI_ERR_CAPACITY, "replicated table too large for 32-bit row indexes");
   u64* buf = nullptr;
   VI_CUDA_TRY(cudaMalloc((void**)&buf, (size_t)total * 32 + 256));
-  cudaError_t e = cudaMemsetAsync(buf, 0, (size_t)total * 32, st);
+  cudaError_t e = cudaMemsetAsync(buf, 0, (size_t)T * 32, st);  // only the shared rows are summed
   if (e == cudaSuccess && rows > 0)
     k_pack_table<<<(rows + 255) / 256, 256, 0, st>>>(ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high,
                                                      rows, T, (u32)my_off, me == 0 ? 1 : 0, buf);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) { cudaFree(buf); return ctx->fail_cuda(e, "pack table", __FILE__, __LINE__); }
-  if (ctx->allreduce(ctx->coll_user, buf, (int64_t)total * 4) != 0)
-  {
-    cudaFree(buf);
-    return ctx->fail(VI_ERR_CUDA, "all-reduce callback failed");
-  }
+  rc = vi_coll_allreduce_u64(ctx, buf, (int64_t)T * 4);
+  if (rc == VI_OK) rc = vi_coll_allgatherv_inplace(ctx, buf, off.data(), len.data());
+  if (rc != VI_OK) { cudaStreamSynchronize(st); cudaFree(buf); return rc; }
   rc = grow_table(ctx, (int64_t)total + 1024, 0);
   if (rc != VI_OK) { cudaFree(buf); return rc; }
   k_unpack_table<<<((u32)total + 255) / 256, 256, 0, st>>>(buf, (u32)total, ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id,
@@ -1393,6 +1355,7 @@ int vi_table_replicate_impl(vi_ctx* ctx)
   ctx->t_rows = (int64_t)total;
   ctx->shared_rows = (int64_t)total;
   ctx->replicated = true;
+  ctx->src_rows = nullptr;  // the vectors stay with their owners
   ctx->info.ranges = (int64_t)total;
   return VI_OK;
 }

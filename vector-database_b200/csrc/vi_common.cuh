@@ -154,12 +154,19 @@ struct vi_ctx
   i64* ids2_buf = nullptr;  int64_t ids2_cap = 0;   // verified ids
   int* search_src = nullptr; int64_t src_cap = 0;   // candidate source rows (only while verifying)
   u32* verify_keep = nullptr; int64_t keep_cap = 0;
+  int64_t pending_nq = -1, pending_total = 0;        // vi_search_begin ... vi_search_fetch
+  float pending_prox = 0.f;
 
   // collective
   int rank = 0, world = 1;
   vi_allreduce_u64_fn allreduce = nullptr;
   vi_alltoallv_fn alltoallv = nullptr;
   void* coll_user = nullptr;
+  void* nccl = nullptr;         // ncclComm_t when the library owns the communicator (vi_comm_init)
+  int64_t coll_calls[3] = {0, 0, 0};  // all-reduce, all-to-all, all-gather: calls and bytes sent (vi_comm_stats)
+  int64_t coll_bytes[3] = {0, 0, 0};
+  void* sh_dev = nullptr;       // multi-rank shared phase: device records (vi_sharded.cuh) and their pinned host copy
+  void* sh_host = nullptr;
   int64_t shared_rows = 0;      // rows of the replicated top levels (multi-rank build), else 0
   bool replicated = false;      // vi_table_replicate done: every rank holds the whole table
   float* own_rows = nullptr;    // multi-rank build: rows / ids of the ranges this rank owns (replace rows/ids as the
@@ -242,6 +249,13 @@ __device__ __forceinline__ u32 hi_before(const FlagScan& f, u32 x)
 
 // build entry points implemented in vi_build.cu / vi_search.cu
 int vi_table_replicate_impl(vi_ctx* ctx);
+// collectives (vi_comm.cu): NCCL on ctx->stream when the library owns a communicator, else the host callbacks
+bool vi_coll_in_stream(const vi_ctx* ctx);
+int vi_coll_allreduce_u64(vi_ctx* ctx, void* d_buf, int64_t count);
+int vi_coll_alltoallv(vi_ctx* ctx, const void* d_send, const int64_t* send_bytes, void* d_recv, const int64_t* recv_bytes);
+int vi_coll_allgather(vi_ctx* ctx, const void* d_send, void* d_recv, int64_t bytes);
+int vi_coll_allgatherv_inplace(vi_ctx* ctx, void* d_buf, const int64_t* offset, const int64_t* bytes);
+void vi_comm_release(vi_ctx* ctx);
 int vi_debug_divcheck_impl(vi_ctx* ctx, uint64_t seed, int64_t samples, int64_t* mismatches);
 int vi_build_impl(vi_ctx* ctx, int mode);
 int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proximity, i64* d_offsets, i64* d_ids,

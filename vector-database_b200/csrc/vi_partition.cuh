@@ -397,10 +397,10 @@ k_children(const LevelDev* __restrict__ cur, u32* __restrict__ ticket, LevelDev*
 
 // per-range child sizes only (shared phase of the multi-rank build: the bookkeeping there follows global sizes)
 __global__ void __launch_bounds__(256)
-k_seg_nlo(SegLevel sg, u32 R, FlagScan fs, u32* __restrict__ seg_nlo, u32* __restrict__ seg_hbase)
+k_seg_nlo(const LevelDev* __restrict__ lvp, SegLevel sg, FlagScan fs, u32* __restrict__ seg_nlo, u32* __restrict__ seg_hbase)
 {
   const u32 s = blockIdx.x * 256u + threadIdx.x;
-  if (s >= R) return;
+  if (s >= lvp->R) return;
   const u32 S = sg.start[s], n = sg.count[s];
   const u32 hb = hi_before(fs, S);
   seg_nlo[s] = n - (hi_before(fs, S + n) - hb);

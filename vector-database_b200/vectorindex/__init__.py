@@ -39,7 +39,7 @@ class BuildInfo(ctypes.Structure):
     _fields_ = [("ranges", ctypes.c_int64), ("levels", ctypes.c_int32), ("mode", ctypes.c_int32),
                 ("point_visits", ctypes.c_int64), ("kernel_launches", ctypes.c_int64), ("build_ms", ctypes.c_double),
                 ("q_exponent", ctypes.c_int32), ("reserved", ctypes.c_int32), ("subtree_ms", ctypes.c_double),
-                ("subtree_ranges", ctypes.c_int64)]
+                ("subtree_ranges", ctypes.c_int64), ("shared_retry", ctypes.c_int32), ("reserved2", ctypes.c_int32)]
 
 
 class LevelInfo(ctypes.Structure):
@@ -54,8 +54,10 @@ ALLTOALLV_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 # every symbol include/vi_b200.h declares
 EXPORTS = ["vi_abi_version", "vi_create", "vi_destroy", "vi_last_error", "vi_points_reserve", "vi_points_add",
            "vi_points_add_device", "vi_points_add_records", "vi_points_add_file", "vi_points_count", "vi_build",
-           "vi_build_levels", "vi_range_count", "vi_ranges_copy", "vi_ranges_load", "vi_textindex_copy", "vi_search", "vi_search_topk", "vi_search_device", "vi_search_verify",
-           "vi_set_collective", "vi_shared_rows", "vi_table_replicate", "vi_table_device", "vi_stream", "vi_debug_divcheck"]
+           "vi_build_levels", "vi_range_count", "vi_ranges_copy", "vi_ranges_load", "vi_textindex_copy", "vi_search", "vi_search_begin",
+           "vi_search_fetch", "vi_search_topk", "vi_search_device", "vi_search_verify",
+           "vi_comm_unique_id", "vi_comm_init", "vi_comm_stats", "vi_set_collective", "vi_shared_rows", "vi_table_replicate",
+           "vi_table_device", "vi_stream", "vi_debug_divcheck"]
 
 _lib = None
 
@@ -93,12 +95,17 @@ def load_library() -> ctypes.CDLL:
                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.vi_search.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, _i64p, _i64p, ctypes.c_int64,
                             _i64p]
+    L.vi_search_begin.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, _i64p]
+    L.vi_search_fetch.argtypes = [vp, _i64p, _i64p, ctypes.c_int64]
     L.vi_search_device.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, vp, vp, ctypes.c_int64,
                                    _i64p, _i64p]
     L.vi_search_verify.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_float, _i64p,
                                    _i64p, ctypes.c_int64, _i64p]
     L.vi_search_topk.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_int32, ctypes.c_int32,
                                  _i64p, _f32p, _i32p, _i64p]
+    L.vi_comm_unique_id.argtypes = [vp, ctypes.c_int32]
+    L.vi_comm_init.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+    L.vi_comm_stats.argtypes = [vp, _i64p, _i64p]
     L.vi_set_collective.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ALLREDUCE_FN, ALLTOALLV_FN, vp]
     L.vi_shared_rows.argtypes = [vp, _i64p]
     L.vi_table_replicate.argtypes = [vp]
@@ -112,6 +119,15 @@ def load_library() -> ctypes.CDLL:
             getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L
+
+
+def comm_unique_id() -> bytes:
+    """128 bytes identifying a new NCCL communicator (call on one rank, hand them to all)."""
+    buf = (ctypes.c_ubyte * 128)()
+    rc = load_library().vi_comm_unique_id(buf, 128)
+    if rc != VI_OK:
+        raise VectorIndexError(rc, "vi_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return bytes(buf)
 
 
 class VectorIndexError(RuntimeError):
@@ -281,9 +297,21 @@ class Context:
         nq, d = queries.shape
         offsets = np.zeros(nq + 1, np.int64)
         total = ctypes.c_int64(0)
-        rc = self._L.vi_search(self._h, _p(queries, _f32p), nq, d, ctypes.c_float(proximity), _p(offsets, _i64p), None,
-                               0, ctypes.byref(total))
-        self._check(rc)
+        self._check(self._L.vi_search_begin(self._h, _p(queries, _f32p), nq, d, ctypes.c_float(proximity), ctypes.byref(total)))
+        ids = np.empty(max(total.value, 1), np.int64)
+        self._check(self._L.vi_search_fetch(self._h, _p(offsets, _i64p), _p(ids, _i64p), ids.shape[0]))
+        return offsets, ids[:total.value]
+
+    def search_two_call(self, queries: np.ndarray, proximity: float):
+        """The size-then-fill protocol of vi_search itself (ids == NULL first, then cap >= total)."""
+        queries = np.ascontiguousarray(queries, np.float32)
+        if queries.ndim == 1:
+            queries = queries[None, :]
+        nq, d = queries.shape
+        offsets = np.zeros(nq + 1, np.int64)
+        total = ctypes.c_int64(0)
+        self._check(self._L.vi_search(self._h, _p(queries, _f32p), nq, d, ctypes.c_float(proximity), _p(offsets, _i64p), None,
+                                      0, ctypes.byref(total)))
         ids = np.empty(max(total.value, 1), np.int64)
         self._check(self._L.vi_search(self._h, _p(queries, _f32p), nq, d, ctypes.c_float(proximity), _p(offsets, _i64p),
                                       _p(ids, _i64p), total.value, ctypes.byref(total)))
@@ -345,6 +373,18 @@ class Context:
 
         self._cb = (ALLREDUCE_FN(_ar), ALLTOALLV_FN(_a2a))  # keep the thunks alive
         self._check(self._L.vi_set_collective(self._h, rank, world, self._cb[0], self._cb[1], None))
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        """Library-owned NCCL communicator (collective call; unique_id: the 128 bytes of comm_unique_id() on rank 0)."""
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(unique_id[:128] if world > 1 else bytes(128))
+        self._check(self._L.vi_comm_init(self._h, buf, 128, rank, world))
+
+    def comm_stats(self):
+        calls = (ctypes.c_int64 * 3)()
+        nbytes = (ctypes.c_int64 * 3)()
+        self._check(self._L.vi_comm_stats(self._h, calls, nbytes))
+        return {"allreduce": calls[0], "alltoallv": calls[1], "allgather": calls[2], "allreduce_bytes": nbytes[0],
+                "alltoallv_bytes": nbytes[1], "allgather_bytes": nbytes[2]}
 
     def replicate(self) -> None:
         """multi-rank: every rank gets the whole table (collective call)"""

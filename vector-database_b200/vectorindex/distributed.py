@@ -1,5 +1,8 @@
-"""torch.distributed plumbing for the multi-rank build: the two collectives libvi_b200 asks its host for
-(include/vi_b200.h vi_set_collective).  One process per GPU; NCCL over NVLink on device buffers.  The same functions
+"""torch.distributed plumbing for the multi-rank build.
+
+`init_nccl(ctx)`: the normal path -- libvi_b200 owns its NCCL communicator (include/vi_b200.h vi_comm_init); torch is
+only used to hand rank 0's 128-byte communicator id to the other ranks.
+`Collectives`: the callback path (vi_set_collective) for hosts that bring their own transport; the same functions
 work on host pointers with the gloo backend, which is how the CPU tests exercise them.
 
 The reference has no counterpart (it is single-process); this is the host half of north_star's
@@ -78,3 +81,17 @@ class Collectives:
 
     def attach(self, ctx) -> None:
         ctx.set_collective(self.rank, self.world, self.allreduce, self.alltoallv)
+
+
+def init_nccl(ctx, device=None, group=None) -> None:
+    """Collective: gives `ctx` a library-owned NCCL communicator spanning the ranks of `group`."""
+    import vectorindex as vi
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    if dist.get_backend(group) == "nccl" and dev.type != "cuda":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(vi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, src=0, group=group)
+    ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
