@@ -40,9 +40,16 @@ enum
 enum
 {
   VI_MODE_EXACT = 0, /* literal float32 sequential Welford, IndexBuilder.cs:175-197: bit-identical range table */
-  VI_MODE_FAST = 1   /* qfx: order-independent exact integer sums of 26-bit fixed-point values,
+  VI_MODE_FAST = 1,  /* qfx: order-independent exact integer sums of 26-bit fixed-point values,
                         HBM-bound, shardable; Mid within 1e-6 * max|x| of the exact mode's */
+  VI_MODE_SQL = 2    /* the rules of the T-SQL builder dbo.BuildIndex (DDL.sql:44-202) over the qfx statistics: max stdev
+                        at depth 0, MIN at depth 1, max below (DDL.sql:113,151,155); the root sends Value = Mean to the
+                        high child (DDL.sql:104); a range whose chosen dimension has Stdev = 0 keeps splitting by ID but
+                        its row has Dimension = null, Mid = null (DDL.sql:193-194) -- Dimension -3 / Mid NaN in
+                        vi_ranges_copy, null in vi_textindex_copy -- and the search follows both its children
+                        (DDL.sql:275,290).  Same kernels, same speed class and sharding as VI_MODE_FAST. */
 };
+#define VI_DIM_NULL (-3) /* vi_ranges_copy / vi_ranges_load: an internal row with Dimension = null (VI_MODE_SQL) */
 
 typedef struct vi_ctx vi_ctx;
 
@@ -138,9 +145,11 @@ int vi_textindex_copy(const vi_ctx* ctx, int64_t* range_id, int16_t* dimension, 
  * and cap < *total (offsets and *total are still valid). */
 int vi_search(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int64_t* offsets,
               int64_t* ids, int64_t cap, int64_t* total);
-/* The same search in two steps that walk the table twice in all (vi_search called twice walks it three times):
- * begin stages the queries and counts (-> *total), fetch fills and copies offsets[nq+1] and ids[*total] (cap >= *total).
- * A build, reserve or another begin in between invalidates the pending search (fetch -> VI_ERR_STATE). */
+/* The same search in two steps: begin stages the queries and counts (-> *total), fetch copies offsets[nq+1] and
+ * ids[*total] (cap >= *total).  Batches whose queries visit many rows (proximity > 0) are walked ONCE, a warp per query:
+ * begin keeps the candidates in a device pool and fetch only gathers them; point-lookup batches are walked one thread
+ * per query, once to count and once to fill.  A build, reserve or any other search call in between invalidates the
+ * pending search (fetch -> VI_ERR_STATE). */
 int vi_search_begin(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, float proximity, int64_t* total);
 int vi_search_fetch(vi_ctx* ctx, int64_t* offsets, int64_t* ids, int64_t cap);
 /* Device-resident form: d_queries, d_offsets[nq+1], d_ids[cap] are device pointers; *total is a host value.

@@ -20,6 +20,7 @@ _LIB_PATH = os.path.join(_HERE, "libvi_oracle.so")
 
 MODE_LITERAL = 0
 MODE_QFX = 1
+MODE_SQL = 2  # dbo.BuildIndex's rules (DDL.sql:44-202) over the qfx statistics; Dimension -3 / Mid NaN = null
 
 _i64p = ctypes.POINTER(ctypes.c_int64)
 _i32p = ctypes.POINTER(ctypes.c_int32)

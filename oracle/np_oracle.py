@@ -76,8 +76,13 @@ def build_literal(ids, rows):
     return out
 
 
-def build_qfx(ids, rows):
-    """The fast-mode specification: exact integer sums of xi = rint(x * 2^(26-E))."""
+def build_qfx(ids, rows, sql=False):
+    """The fast-mode specification: exact integer sums of xi = rint(x * 2^(26-E)).
+
+    sql=True: dbo.BuildIndex's rules (DDL.sql:44-202) over the same statistics -- `order by Stdev desc` at the root
+    (:113), `iif(@level % 2 = 1, Stdev, -Stdev) desc` with @level = 0, 1, 3, 7, ... below it (:151,155): min at depth 1,
+    max everywhere else; the root sends Value = Mean high unless Stdev = 0 (:104); Stdev = 0 nulls Dimension and Mid
+    (:193-194), written -3 / NaN."""
     rows = np.asarray(rows, np.float32)
     ids = [int(i) for i in ids]
     finite = np.abs(rows[np.isfinite(rows)])
@@ -106,6 +111,10 @@ def build_qfx(ids, rows):
         if n == 1:
             out.append((range_id, -1, np.float32(0), idn))
             continue
+        depth = (range_id + 1).bit_length() - 1
+        if sql:
+            mx = depth != 1
+        stdev_zero = False
         sub = xi[pts]
         s1 = [int(v) for v in sub.sum(axis=0)]
         s2 = [sum(int(v) * int(v) for v in sub[:, j]) for j in range(sub.shape[1])]
@@ -130,6 +139,7 @@ def build_qfx(ids, rows):
                 if _cmp_dotnet(fk[i], fk[index]) > 0:
                     index = i
             mid = mean[index]
+            stdev_zero = sql and q[index] == 0
         else:
             index = 0
             for i in range(1, len(keys)):
@@ -137,11 +147,12 @@ def build_qfx(ids, rows):
                     index = i
             mid = np.float32((np.float64(s1[index]) / np.float64(n)) * np.float64(2.0) ** (e - 26))
         pivot = _trunc_div(idn, n)
-        out.append((range_id, index, mid, pivot))
+        out.append((range_id, -3, np.float32(np.nan), pivot) if stdev_zero else (range_id, index, mid, pivot))
+        root_ties_high = sql and depth == 0 and not stdev_zero
         lo, hi = [], []
         for p in pts:
             value = rows[p, index]
-            if value > mid or (value == mid and ids[p] > pivot):
+            if value > mid or (value == mid and (root_ties_high or ids[p] > pivot)):
                 hi.append(p)
             else:
                 lo.append(p)
@@ -162,6 +173,10 @@ def search(table: dict, query, proximity):
         if row is None:
             continue
         dim, mid, rid = row
+        if dim == -3:  # Dimension is null (DDL.sql:275,290): both children
+            stack.append(2 * r + 2)
+            stack.append(2 * r + 1)
+            continue
         if dim < 0:
             out.append(rid)
             continue

@@ -29,6 +29,21 @@
  *   mode 1  "qfx":     the B200 fast mode's *specification* (order-independent fixed-point integer sums),
  *                      restated on the CPU so the GPU fast path can be checked bit-exactly against it.  It is
  *                      not the reference's arithmetic; tests report its divergence from mode 0.
+ *   mode 2  "sql":     the rules of the T-SQL builder dbo.BuildIndex (DDL.sql:44-202) over the qfx statistics:
+ *                      - max stdev at depth 0, MIN at depth 1, max at every depth >= 2: `iif(@level % 2 = 1, Stdev,
+ *                        -Stdev) desc` with @level = 0, 1, 3, 7, ... (DDL.sql:113,151,155);
+ *                      - the root sends Value = Mean to the HIGH child whatever the id (DDL.sql:104, `iif(Value <
+ *                        Mean, 1, 2)`); deeper levels use Value < Mean / Value > Mean / ID <= avg(ID) (DDL.sql:161-167),
+ *                        which is IndexBuilder's predicate;
+ *                      - a range whose chosen dimension has Stdev = 0 keeps splitting by ID but its row has
+ *                        Dimension = null, Mid = null (DDL.sql:193-194): here Dimension -3, Mid NaN, and dbo.Search
+ *                        follows both children of such a row (DDL.sql:275,290 `N.Dimension is null or ...`);
+ *                      - avg(ID) is the truncating bigint average, as IndexBuilder's Int128 one.
+ *                      SQL Server's float(53) avg / stdev aggregate in an unspecified order, and `top 1 ... order by
+ *                      Stdev` breaks ties arbitrarily: the statistics here are the qfx integer sums (order-free, Mean
+ *                      within 2^-27 * 2^E of the exact average), ties go to the lowest dimension, and "Stdev = 0" is
+ *                      decided where the qfx rules already hand a poorly resolved range to the float32 recurrence
+ *                      (its Stdev2N == 0, i.e. all values of the chosen dimension are equal).
  */
 #include <math.h>
 #include <stdint.h>
@@ -139,7 +154,8 @@ int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
                  int64_t cap, int64_t* out_range_id, int32_t* out_dim, float* out_mid, int64_t* out_id,
                  int64_t* out_count, int64_t root_rid, int root_max, int32_t qe_override)
 {
-  if (n < 0 || d <= 0 || ld < d || (mode != 0 && mode != 1)) return VIO_ERR_ARG;
+  if (n < 0 || d <= 0 || ld < d || (mode != 0 && mode != 1 && mode != 2)) return VIO_ERR_ARG;
+  const int sql = (mode == 2);
   *out_count = 0;
   if (n == 0) return VIO_OK; /* IndexBuilder.cs:70-73 : empty root emits nothing */
 
@@ -157,7 +173,7 @@ int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
   int qe = 0;
   float qk = 1.0f;
   double qinv = 1.0;
-  if (mode == 1)
+  if (mode != 0)
   {
     qe = qe_override != INT32_MIN ? qe_override : vio_qfx_exponent(rows, n, d, ld);
     qk = ldexpf(1.0f, VIO_QBITS - qe);
@@ -180,7 +196,11 @@ int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
     float mid = 0.0f;
 
     int literal = (mode == 0);
-    if (mode == 1)
+    int depth = 0;
+    for (uint64_t t = (uint64_t)it.range_id + 1; t > 1; t >>= 1) ++depth;
+    if (sql) it.max = (depth != 1); /* DDL.sql:113 (root: Stdev desc), :151 with @level = 0, 1, 3, 7, ... (:155) */
+    int null_dim = 0;
+    if (mode != 0)
     {
       /* qfx specification (DESIGN.md "fast mode"): exact integer sums of xi = rint(x * 2^(26-E)). */
       for (int32_t i = 0; i < d; ++i) { s1[i] = 0; s2[i] = 0; }
@@ -241,6 +261,7 @@ int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
         if (cmp_float_dotnet(key, best) > 0) { best = key; index = i; }
       }
       mid = mean[index];
+      if (sql && q[index] == 0.0f) null_dim = 1; /* Stdev = 0 (DDL.sql:193-194) */
     }
 
     if (emitted >= cap) { rc = VIO_ERR_CAPACITY; goto done; }
@@ -255,10 +276,13 @@ int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
       continue; /* IndexBuilder.cs:94-97 */
     }
     int64_t pivot = (int64_t)(idn / (i128)count); /* IndexBuilder.cs:87, truncation toward zero */
-    out_dim[emitted] = index;
-    out_mid[emitted] = mid;
+    out_dim[emitted] = null_dim ? -3 : index;
+    out_mid[emitted] = null_dim ? NAN : mid;
     out_id[emitted] = pivot;
     ++emitted;
+    /* dbo.BuildIndex root (DDL.sql:104): `iif(S.Stdev = 0, iif(P.ID <= S.ID, 1, 2), iif(Value < Mean, 1, 2))` -- a
+     * value equal to the mean goes high whatever its id (ids are > INT64_MIN) */
+    if (sql && depth == 0 && !null_dim) pivot = INT64_MIN;
 
     /* IndexBuilder.cs:99,104 checked arithmetic */
     if (it.range_id > (INT64_MAX - 2) / 2) { rc = VIO_ERR_OVERFLOW; goto done; }
@@ -325,7 +349,7 @@ int vio_search(int64_t nrows, const int64_t* range_id, const int32_t* dim, const
     if (row < 0) continue; /* join finds no I row */
     ++visits;
     int32_t k = dim[row];
-    if (k < 0)
+    if (k < 0 && k != -3)
     {
       if (found < cap) out_ids[found] = id[row];
       ++found;
@@ -333,9 +357,17 @@ int vio_search(int64_t nrows, const int64_t* range_id, const int32_t* dim, const
     }
     if (k >= d) { free(st.items); return VIO_ERR_ARG; }
     if (r > (INT64_MAX - 2) / 2) continue;
+    work_item c = {0, 0, 0, 0};
+    if (k == -3)
+    {
+      /* a dbo.BuildIndex row with Dimension = null (mode 2): `N.Dimension is null or ...` follows both children
+       * (DDL.sql:275,290) */
+      c.range_id = 2 * r + 2; if (!push(&st, c)) { free(st.items); return VIO_ERR_NOMEM; }
+      c.range_id = 2 * r + 1; if (!push(&st, c)) { free(st.items); return VIO_ERR_NOMEM; }
+      continue;
+    }
     float lo = query[k] - proximity; /* DDL.sql:249-250, SQL `real` arithmetic */
     float hi = query[k] + proximity;
-    work_item c = {0, 0, 0, 0};
     /* push high first so that low is visited first */
     if (mid[row] <= hi) { c.range_id = 2 * r + 2; if (!push(&st, c)) { free(st.items); return VIO_ERR_NOMEM; } } /* DDL.sql:280-293 */
     if (mid[row] >= lo) { c.range_id = 2 * r + 1; if (!push(&st, c)) { free(st.items); return VIO_ERR_NOMEM; } } /* DDL.sql:265-278 */

@@ -540,3 +540,52 @@ def test_one_million_points_bit_exact(mode):
     ids, rows = ds.unit_gaussian(1_000_000, 96, seed=61)
     info = assert_same_table(ids, rows, mode)
     assert info.levels >= 20
+
+
+# ---- warp-per-query traversal: forced paths, stack spill, pool overflow ---------------------------------------------
+_SEARCH_PATHS_CASE = []
+
+
+def _search_paths_case():
+    if not _SEARCH_PATHS_CASE:
+        ids, rows = ds.unit_gaussian(60_000, 24, seed=12)
+        _, fresh = ds.unit_gaussian(200, 24, seed=13)
+        queries = np.concatenate([rows[:200], fresh], 0)
+        ref = oracle.build(ids, rows, oracle.MODE_QFX)
+        want = {p: oracle.search(ref, queries, p)[:2] for p in (0.0, 0.02, 0.1, 0.5)}
+        _SEARCH_PATHS_CASE.append((ids, rows, queries, ref, want))
+    return _SEARCH_PATHS_CASE[0]
+
+
+@pytest.mark.parametrize("env", [
+    {"VI_B200_SEARCH_PATH": "0"},                                        # one thread per query, count + fill
+    {"VI_B200_SEARCH_PATH": "1"},                                        # warp per query, candidate pool + gather
+    {"VI_B200_SEARCH_PATH": "1", "VI_B200_SEARCH_POOL": "0"},            # warp per query, count + fill
+    {"VI_B200_SEARCH_PATH": "1", "VI_B200_SEARCH_STACK": "64"},          # shared stack spills to global memory
+    {"VI_B200_SEARCH_PATH": "1", "VI_B200_SEARCH_POOL_SLOTS": "4096"},   # pool overflows: the rest is walked again
+])
+def test_search_paths_agree_with_the_oracle(env, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ids, rows, queries, ref, want = _search_paths_case()
+    with vi.Context(0) as ctx:
+        ctx.reserve(len(ids), 24)
+        ctx.add(ids, rows)
+        ctx.build(vi.MODE_FAST)
+        for p in (0.0, 0.02, 0.1, 0.5):
+            roffs, rout = want[p]
+            offs, out = ctx.search(queries, p)
+            assert np.array_equal(offs, roffs), p
+            assert np.array_equal(out, rout), p
+            offs, out = ctx.search_two_call(queries, p)
+            assert np.array_equal(offs, roffs) and np.array_equal(out, rout), p
+        # p = 0.5 on 24 dims: tens of thousands of candidates per query (deep pending lists)
+        assert len(rout) > 200 * 10_000
+        # verification and top-k walk with source rows (no pool)
+        dist = 0.25
+        voffs, vout = ctx.search_verify(queries[:50], 0.1, dist)
+        roffs, rout, _ = oracle.search(ref, queries[:50], 0.1)
+        for i in range(50):
+            cand = rout[roffs[i]:roffs[i + 1]]
+            want = [int(k) for k in cand if oracle.distance_l2(rows[k], queries[i]) <= np.float32(dist)]
+            assert vout[voffs[i]:voffs[i + 1]].tolist() == want

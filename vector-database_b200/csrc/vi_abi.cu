@@ -75,6 +75,7 @@ void vi_destroy(vi_ctx* ctx)
   free_points(ctx);
   cudaFree(ctx->q_buf); cudaFree(ctx->off_buf); cudaFree(ctx->ids_buf); cudaFree(ctx->off2_buf);
   cudaFree(ctx->ids2_buf); cudaFree(ctx->search_src); cudaFree(ctx->verify_keep);
+  cudaFree(ctx->sw_pool); cudaFree(ctx->sw_head); cudaFree(ctx->sw_spill);
   cudaFree(ctx->own_rows); cudaFree(ctx->own_ids); cudaFree(ctx->send_rows); cudaFree(ctx->send_ids);
   vi_comm_release(ctx);
   cudaFree(ctx->sh_dev);
@@ -332,6 +333,7 @@ int vi_search_device(vi_ctx* ctx, const float* d_queries, int64_t nq, int32_t di
   if (nq < 0 || nq >= (int64_t)0x7fffffff || (nq > 0 && !d_queries) || !d_offsets)
     return ctx->fail(VI_ERR_INVALID_ARG, "bad query batch");
   VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->pending_nq = -1;  // a pending vi_search_begin shares the candidate pool with this call
   int* keep_src = ctx->search_src;
   ctx->search_src = nullptr;  // plain search does not record source rows
   int rc = vi_search_impl(ctx, d_queries, nq, proximity, d_offsets, d_ids, cap, total, visits, false);
@@ -467,7 +469,9 @@ int vi_search_verify(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims
   int64_t cand = 0;
   int* keep_src = ctx->search_src;
   ctx->search_src = nullptr;
+  ctx->search_want_src = true;  // the fill pass records source rows: count only, no candidate pool
   rc = vi_search_impl(ctx, ctx->q_buf, nq, proximity, ctx->off_buf, nullptr, 0, &cand, nullptr, false);
+  ctx->search_want_src = false;
   ctx->search_src = keep_src;
   if (rc != VI_OK) return rc;
   rc = grow(ctx, &ctx->ids_buf, &ctx->ids_cap, cand + 1);

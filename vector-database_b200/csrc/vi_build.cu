@@ -342,6 +342,7 @@ struct BuildEnv
 {
   int mode;
   u32 t_team, t_big, big_unroll;
+  u32 t_slot;   // ranges of >= t_slot points get a big-list slot (their sums can be kept / derived); t_slot <= t_big
   u32 sibling;  // fast mode: sum only the smaller child of a big pair, derive the other from the parent (1 = on)
   u32 t_sub;    // ranges of 2..t_sub points are finished by the sub-tree kernel (0 = off)
   u32 sub_minb;
@@ -393,6 +394,10 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
   env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 8, 0, 8);  // 0 = cp.async ring
   env.sibling = env_u32("VI_B200_SIBLING", 1, 0, 1);
+  // sibling derivation reaches below the chunked class: a warp-per-range range of >= t_slot points keeps its sums when
+  // its children may pair up, and the larger child of such a pair is derived instead of summed
+  env.t_slot = (mode == VI_MODE_FAST && env.sibling) ? std::min(env.t_big, env_u32("VI_B200_T_SLOT", 128, VI_MIN_BIG, 1u << 30))
+                                                     : env.t_big;
   // sub-tree kernel (fast mode, vi_subtree.cuh): a range of up to t_sub points is finished by one warp in shared
   // memory; as many rows as fit 12.5 KB per warp (8 warps per CTA, 2 CTAs per SM), at most 32 (one point per lane)
   {
@@ -609,21 +614,17 @@ static int enqueue_level(vi_ctx* ctx, BuildEnv& env, const LevelState& b, int le
   // ---- statistics + split choice ---------------------------------------------------------------------------
   if (mode == VI_MODE_FAST)
   {
-    if (b.nbig)
+    const u32 t_slot = env.t_slot;
+    const bool chunked = b.nbig && b.maxseg >= t_big;
+    if (chunked)
     {
-      VI_CUDA_TRY(cudaMemsetAsync(gacc_cur, 0, (size_t)b.nbig * env.gstride * sizeof(u64), st));
-      launch_big_fast(ctx, env, lvp, rows, cur, b.chunks, mx, 1, gacc_cur, env.sibling ? 2 * t_big : 0xffffffffu,
+      // gacc is accumulated with atomics only by ranges of several chunks (or column passes); every other record is
+      // written whole by whoever keeps it
+      const int single_pass0 = (ld / 4) <= env.shp_big.ts * env.shp_big.ch;
+      if (b.maxseg > VI_CHUNK || !single_pass0)
+        VI_CUDA_TRY(cudaMemsetAsync(gacc_cur, 0, (size_t)b.nbig * env.gstride * sizeof(u64), st));
+      launch_big_fast(ctx, env, lvp, rows, cur, b.chunks, mx, 1, gacc_cur, env.sibling ? 2 * t_slot : 0xffffffffu,
                       env.sibling ? ctx->bl_sib[cur] : nullptr);
-      // derived ranges (parent - sibling), ranges that span several chunks or column passes: split choice from gacc;
-      // ranges that fit one chunk and one column pass were finished by their CTA
-      const int single_pass = (ld / 4) <= env.shp_big.ts * env.shp_big.ch;
-      if (!single_pass || b.maxseg > VI_CHUNK || env.sibling)
-      {
-        k_finalize_big_fast<<<(b.nbig * 32 + 255) / 256, 256, 0, st>>>(
-            lvp, sg, ctx->big_list[cur], gacc_cur, gacc_prev, ld, dims, env.qinv, mx, sout, rows, ctx->perm[cur], single_pass,
-            0, nullptr, env.sibling ? ctx->bl_parent[cur] : nullptr, ctx->bl_sib[cur]);
-        ++env.launches;
-      }
     }
     // warp-per-range class (teams of a warp share one range); for TS == 32 it also covers the team class.
     // Below the first level of a loop every range has more than t_sub points (smaller children went to the sub-tree
@@ -633,19 +634,35 @@ static int enqueue_level(vi_ctx* ctx, BuildEnv& env, const LevelState& b, int le
     const bool may_warp = std::max(wlo, floor_n) < t_big && b.maxseg >= wlo && (!exact_sizes || b.minseg < t_big);
     if (may_warp)
     {
+      u64* wg = (env.sibling && b.nbig) ? gacc_cur : nullptr;
 #define CALL_WARP(TS, CH, FULL)                                                                              \
   k_stats_small_fast<TS, CH, FULL, true><<<(u32)(((u64)b.R * 32 + 255) / 256), 256, 0, st>>>(                 \
-      lvp, sg, wlo, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout)
+      lvp, sg, wlo, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout, wg,      \
+      ctx->bl_parent[cur], ctx->bl_sib[cur], 2 * t_slot)
       FAST_DISPATCH(shp, CALL_WARP);
 #undef CALL_WARP
       ++env.launches;
+    }
+    if (b.nbig)
+    {
+      // derived ranges (parent - sibling), ranges that span several chunks or column passes: split choice from gacc;
+      // ranges that fit one chunk and one column pass were finished by their CTA, smaller ones by their warp
+      const int single_pass = (ld / 4) <= env.shp_big.ts * env.shp_big.ch;
+      if (!single_pass || b.maxseg > VI_CHUNK || env.sibling)
+      {
+        k_finalize_big_fast<<<(b.nbig * 32 + 255) / 256, 256, 0, st>>>(
+            lvp, sg, ctx->big_list[cur], gacc_cur, gacc_prev, ld, dims, env.qinv, mx, sout, rows, ctx->perm[cur], single_pass,
+            0, nullptr, env.sibling ? ctx->bl_parent[cur] : nullptr, ctx->bl_sib[cur], t_big);
+        ++env.launches;
+      }
     }
     const bool may_team = shp.ts < 32 && floor_n < t_team && (!exact_sizes || b.minseg < t_team);
     if (may_team)
     {
 #define CALL_TEAM(TS, CH, FULL)                                                                              \
   k_stats_small_fast<TS, CH, FULL, false><<<(u32)(((u64)b.R * TS + 255) / 256), 256, 0, st>>>(                \
-      lvp, sg, 2u, t_team, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout)
+      lvp, sg, 2u, t_team, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout, nullptr, nullptr, \
+      nullptr, 0xffffffffu)
       FAST_DISPATCH(shp, CALL_TEAM);
 #undef CALL_TEAM
       ++env.launches;
@@ -731,14 +748,14 @@ static int enqueue_level(vi_ctx* ctx, BuildEnv& env, const LevelState& b, int le
                                             ctx->fbits, ctx->wloc, ctx->ftile);
   k_children<<<(b.R + CH_TILE - 1) / CH_TILE, 256, 0, st>>>(lvp, &lvp->ticket[1], lvp + 1, ctx->h_lv + level + 1, sg, fs,
                                                            ctx->seg_nlo, ctx->seg_hbase, ctx->c_pre, ctx->ctile,
-                                                           ctx->ctile_mm, env.t_sub, t_big, sibling, (u32)ctx->t_cap,
-                                                           ctx->chunk_first[nxt]);
+                                                           ctx->ctile_mm, env.t_sub, env.t_slot, t_big, sibling,
+                                                           (u32)ctx->t_cap, ctx->chunk_first[nxt]);
   NextLevel nx{ctx->seg[nxt], ctx->perm[nxt], ctx->pid[nxt], ctx->seg_of[nxt], ctx->big_list[nxt], ctx->bl_parent[nxt],
                ctx->bl_sib[nxt], ctx->chunk_first[nxt]};
   SubList sl{ctx->sub_start, ctx->sub_count, ctx->sub_rid, ctx->sub_row, ctx->sub_depth};
   k_scatter<<<(b.A + 255) / 256, 256, 0, st>>>(lvp, lvp + 1, sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur], fs,
-                                               ctx->seg_nlo, ctx->seg_hbase, ctx->c_pre, ctx->ctile, env.t_sub, t_big, sibling,
-                                               (u32)level + 1u, nx, tout, ctx->t_src, sl, ctx->sub_perm, ctx->sub_pid);
+                                               ctx->seg_nlo, ctx->seg_hbase, ctx->c_pre, ctx->ctile, env.t_sub, env.t_slot, t_big,
+                                               sibling, (u32)level + 1u, nx, tout, ctx->t_src, sl, ctx->sub_perm, ctx->sub_pid);
   env.launches += 3;
   ev.e2 = env_event(ctx, env);
   return VI_OK;
@@ -829,8 +846,8 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
     {
       const u64 grow = 1ull << d;
       b.R = (u32)std::min<u64>((u64)known.R * grow, (u64)known.A / 2);
-      b.nbig = (u32)std::min<u64>((u64)known.nbig * grow, (u64)known.A / t_big);
-      b.chunks = known.A / VI_CHUNK + b.nbig;
+      b.nbig = (u32)std::min<u64>((u64)known.nbig * grow, (u64)known.A / env.t_slot);
+      b.chunks = known.A / VI_CHUNK + std::min<u32>(b.nbig, known.A / t_big);
       b.minseg = 2;
     }
     LevelEvents ev;
@@ -1063,7 +1080,7 @@ static int build_sharded_try(vi_ctx* ctx, BuildEnv& env, int Lcap, int* retry_le
     if ((rc = vi_coll_allreduce_u64(ctx, ctx->gacc, (int64_t)((size_t)Rb * env.gstride)))) return rc;
     k_finalize_big_fast<<<(Rb * 32 + 255) / 256, 256, 0, st>>>(lvp, sg, ctx->big_list[cur], ctx->gacc, nullptr, ld, dims,
                                                                env.qinv, mx, sout, ctx->rows, ctx->perm[cur], 0, 1,
-                                                               &sd->stat_err, nullptr, nullptr);
+                                                               &sd->stat_err, nullptr, nullptr, 0u);
     ev.e1 = env_event(ctx, env);
     // local partition flags and child sizes; global child sizes; children (identical on every rank); local scatter
     k_flags<<<nloc / FL_TILE + 1, 256, 0, st>>>(lvp, &lvp->ticket[0], sg, ctx->seg_of[cur], ctx->perm[cur], ctx->pid[cur],

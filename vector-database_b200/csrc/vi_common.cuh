@@ -16,7 +16,7 @@ typedef unsigned __int128 u128;
 
 // Ranges with at least t_big points are "big": their statistics are computed by many CTAs (fast mode) or by one
 // thread per (range, dimension) chain (exact mode); smaller ranges are owned by one team/warp (vi_build.cu).
-constexpr u32 VI_MIN_BIG = 256;  // smallest allowed "big range" threshold (sizes the big-range work space)
+constexpr u32 VI_MIN_BIG = 64;   // smallest allowed "big range" threshold (sizes the big-range work space)
 // Rows of a big range handled by one CTA of the fast-mode statistics kernel.
 constexpr u32 VI_CHUNK = 4096;
 constexpr int VI_NUM_SMS = 148;
@@ -156,6 +156,16 @@ struct vi_ctx
   u32* verify_keep = nullptr; int64_t keep_cap = 0;
   int64_t pending_nq = -1, pending_total = 0;        // vi_search_begin ... vi_search_fetch
   float pending_prox = 0.f;
+  // warp-per-query traversal (vi_search.cu): candidate pool of the single-pass form, per-query chunk heads, per-warp
+  // stack spill area, control words
+  i64* sw_pool = nullptr;    int64_t sw_pool_cap = 0;   // slots (chunks of SW_CHUNK: [link][63 ids])
+  i64* sw_head = nullptr;    int64_t sw_head_cap = 0;
+  u32* sw_spill = nullptr;   int64_t sw_spill_cap = 0;
+  int search_path = 0;                                  // of the last count pass: 0 = thread per query, 1 = warp per query
+  bool search_want_src = false;                         // the caller will fill with source rows (verify / top-k): no pool
+  bool sw_pool_valid = false;                           // the pool holds the candidates of (sw_q, sw_off, sw_nq, sw_prox)
+  bool sw_pool_overflow = false;
+  const float* sw_q = nullptr; const i64* sw_off = nullptr; int64_t sw_nq = 0; float sw_prox = 0.f;
 
   // collective
   int rank = 0, world = 1;

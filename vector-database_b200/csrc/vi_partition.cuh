@@ -111,12 +111,16 @@ struct Children
   u32 nlo, nhi;
   bool lo_sub, hi_sub;          // 2..t_sub points: finished by the sub-tree kernel
   bool lo_act, hi_act;          // more: a range of the next level
-  bool lo_big, hi_big;          // >= t_big points
-  bool pair;                    // both big and the parent's integer sums are kept: only the smaller one is summed
+  bool lo_big, hi_big;          // >= t_slot points: the range gets a slot of the level's big list (its integer sums
+                                //   can be kept in gacc); of those, ranges of >= t_big points are summed in chunks
+  bool pair;                    // both slotted and the parent's integer sums are kept: only the smaller one is summed
   bool lo_derived, hi_derived;  // the larger one's sums are parent - sibling (ties: low is summed)
+  u32 lo_chunks, hi_chunks;     // chunk CTAs of the statistics kernel
 };
 
-__device__ __forceinline__ Children classify_children(u32 n, u32 nlo, u32 t_sub, u32 t_big, bool can_pair)
+__device__ __forceinline__ u32 chunks_of(u32 n) { return (n + VI_CHUNK - 1) / VI_CHUNK; }
+
+__device__ __forceinline__ Children classify_children(u32 n, u32 nlo, u32 t_sub, u32 t_slot, u32 t_big, bool can_pair)
 {
   Children c;
   c.nlo = nlo;
@@ -125,15 +129,15 @@ __device__ __forceinline__ Children classify_children(u32 n, u32 nlo, u32 t_sub,
   c.hi_sub = c.nhi >= 2 && c.nhi <= t_sub;
   c.lo_act = c.nlo > 1 && !c.lo_sub;
   c.hi_act = c.nhi > 1 && !c.hi_sub;
-  c.lo_big = c.lo_act && c.nlo >= t_big;
-  c.hi_big = c.hi_act && c.nhi >= t_big;
+  c.lo_big = c.lo_act && c.nlo >= t_slot;
+  c.hi_big = c.hi_act && c.nhi >= t_slot;
   c.pair = can_pair && c.lo_big && c.hi_big;
   c.lo_derived = c.pair && c.nlo > c.nhi;
   c.hi_derived = c.pair && c.nlo <= c.nhi;
+  c.lo_chunks = (c.lo_big && !c.lo_derived && c.nlo >= t_big) ? chunks_of(c.nlo) : 0u;
+  c.hi_chunks = (c.hi_big && !c.hi_derived && c.nhi >= t_big) ? chunks_of(c.nhi) : 0u;
   return c;
 }
-
-__device__ __forceinline__ u32 chunks_of(u32 n) { return (n + VI_CHUNK - 1) / VI_CHUNK; }
 
 __device__ __forceinline__ ChildAgg child_counts(const Children& c)
 {
@@ -144,7 +148,7 @@ __device__ __forceinline__ ChildAgg child_counts(const Children& c)
   a.sub_cnt = (u32)c.lo_sub + (u32)c.hi_sub;
   a.sub_pos = (c.lo_sub ? c.nlo : 0u) + (c.hi_sub ? c.nhi : 0u);
   a.big_cnt = (u32)c.lo_big + (u32)c.hi_big;
-  a.chunks = ((c.lo_big && !c.lo_derived) ? chunks_of(c.nlo) : 0u) + ((c.hi_big && !c.hi_derived) ? chunks_of(c.nhi) : 0u);
+  a.chunks = c.lo_chunks + c.hi_chunks;
   a.derived = (c.lo_derived ? c.nlo : 0u) + (c.hi_derived ? c.nhi : 0u);
   return a;
 }
@@ -276,8 +280,8 @@ static_assert((1 << CH_TILE_LOG2) == CH_TILE, "tile size");
 __global__ void __launch_bounds__(256)
 k_children(const LevelDev* __restrict__ cur, u32* __restrict__ ticket, LevelDev* __restrict__ nxt, LevelDev* __restrict__ h_nxt,
            SegLevel sg, FlagScan fs, u32* __restrict__ seg_nlo, u32* __restrict__ seg_hbase, ChildAgg* __restrict__ c_pre,
-           ChildAgg* __restrict__ ctile, uint2* __restrict__ ctile_mm, u32 t_sub, u32 t_big, int sibling, u32 t_cap,
-           u32* __restrict__ chunk_first_next)
+           ChildAgg* __restrict__ ctile, uint2* __restrict__ ctile_mm, u32 t_sub, u32 t_slot, u32 t_big, int sibling,
+           u32 t_cap, u32* __restrict__ chunk_first_next)
 {
   __shared__ ChildAgg s_w[8];
   __shared__ u32 s_min[8], s_max[8];
@@ -319,7 +323,7 @@ k_children(const LevelDev* __restrict__ cur, u32* __restrict__ ticket, LevelDev*
       const u32 nlo = n - nhi;
       seg_nlo[s] = nlo;
       seg_hbase[s] = hb;
-      const Children c = classify_children(n, nlo, t_sub, t_big, sibling && sg.bslot[s] != VI_NOSLOT);
+      const Children c = classify_children(n, nlo, t_sub, t_slot, t_big, sibling && sg.bslot[s] != VI_NOSLOT);
       run = agg_add(run, child_counts(c));
       if (c.lo_act) { mn = min(mn, nlo); mx = max(mx, nlo); }
       if (c.hi_act) { mn = min(mn, nhi); mx = max(mx, nhi); }
@@ -424,7 +428,8 @@ __global__ void __launch_bounds__(256)
 k_scatter(const LevelDev* __restrict__ cur, const LevelDev* __restrict__ nxt, SegLevel sg, const u32* __restrict__ seg_of,
           const u32* __restrict__ perm, const i64* __restrict__ pid, FlagScan fs, const u32* __restrict__ seg_nlo,
           const u32* __restrict__ seg_hbase, const ChildAgg* __restrict__ c_pre, const ChildAgg* __restrict__ ctile,
-          u32 t_sub, u32 t_big, int sibling, u32 child_depth, NextLevel nx, TableOut t, int* __restrict__ t_src, SubList sub,
+          u32 t_sub, u32 t_slot, u32 t_big, int sibling, u32 child_depth, NextLevel nx, TableOut t, int* __restrict__ t_src,
+          SubList sub,
           u32* __restrict__ sub_perm, i64* __restrict__ sub_pid)
 {
   const u32 p = blockIdx.x * 256u + threadIdx.x;
@@ -432,7 +437,7 @@ k_scatter(const LevelDev* __restrict__ cur, const LevelDev* __restrict__ nxt, Se
   const u32 s = seg_of[p];
   const u32 S = sg.start[s], n = sg.count[s];
   const u32 parent_slot = sibling ? sg.bslot[s] : VI_NOSLOT;
-  const Children c = classify_children(n, seg_nlo[s], t_sub, t_big, parent_slot != VI_NOSLOT);
+  const Children c = classify_children(n, seg_nlo[s], t_sub, t_slot, t_big, parent_slot != VI_NOSLOT);
   const ChildAgg P = agg_add(agg_load(c_pre + s), agg_load(ctile + (s >> CH_TILE_LOG2)));
   const u32 r0 = cur->row_next + P.rows;      // first child row
   const u32 a0 = P.act_cnt, p0 = P.act_pos;   // next-level range index / first position of the first staying child
@@ -495,7 +500,7 @@ k_scatter(const LevelDev* __restrict__ cur, const LevelDev* __restrict__ nxt, Se
   t.t_high[row] = hi_row;
   const u32 lo_slot = c.lo_big ? P.big_cnt : VI_NOSLOT;
   const u32 hi_slot = c.hi_big ? P.big_cnt + (c.lo_big ? 1u : 0u) : VI_NOSLOT;
-  const u32 lo_chunks = (c.lo_big && !c.lo_derived) ? chunks_of(nlo) : 0u;
+  const u32 lo_chunks = c.lo_chunks;
   if (nlo > 0)
   {
     t.t_rid[lo_row] = rid * 2 + 1;  // IndexBuilder.cs:99

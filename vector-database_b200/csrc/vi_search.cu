@@ -9,6 +9,9 @@
 // Candidate verification (the predicate half of Find, MemoryVectorIndex.cs:237-241,336-342): Euclidean distance
 // with float32 accumulation in index order, as MemoryVectorIndexTests.cs:209-217, one thread per candidate so the
 // summation order is the oracle's.
+#include <algorithm>
+#include <cstdlib>
+
 #include "vi_common.cuh"
 
 template <typename T>
@@ -66,17 +69,19 @@ __global__ void __launch_bounds__(1024) k_scan_i64(i64* a, u32 n)
   if (threadIdx.x == 0) a[n] = carry_s;
 }
 
+// `stride`: the thread's query is i * stride (the sampling pass that picks the traversal kernel walks every
+// stride-th query; the passes proper use stride 1)
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k_search(const int4* __restrict__ node, const int* __restrict__ t_src, const float* __restrict__ queries, int ldq,
-         u32 nq, float prox, i64* __restrict__ offsets, i64* __restrict__ ids_out, int* __restrict__ src_out,
+         u32 nq, u32 stride, float prox, i64* __restrict__ offsets, i64* __restrict__ ids_out, int* __restrict__ src_out,
          i64 cap, unsigned long long* __restrict__ visits)
 {
   const u32 i = blockIdx.x * 128u + threadIdx.x;
   unsigned long long v = 0;
   if (i < nq)
   {
-    const float* q = queries + (size_t)i * ldq;
+    const float* q = queries + (size_t)i * stride * ldq;
     u32 stack[64];
     int sp = 0;
     stack[sp++] = 0u;
@@ -115,13 +120,328 @@ k_search(const int4* __restrict__ node, const int* __restrict__ t_src, const flo
   }
 }
 
+// ---- warp per query: the per-warp frontier stack -------------------------------------------------------------------
+// Queries that visit many rows (proximity > 0: ~2000 rows and ~600 candidates per query at 10M x 96, p = 0.01) are
+// walked by a whole warp.  The pending rows of a query form ONE list in the oracle's DFS order (low branch first):
+//   frontier (<= 32 rows, one per lane, in shared memory)  ++  stack (top first; shared memory, spilling to global).
+// A round: every lane loads the packed row of its frontier entry (32 independent loads in flight per warp); the
+// leaves at the head of the list are final and are written out together, in order (coalesced); every other entry is
+// replaced in place by itself (a leaf waiting for its turn, flagged so that it is not loaded again until then) or by
+// the children the query's box reaches (low, then high).  The first 32 entries of the new list stay the frontier, the
+// rest goes back on the stack in reverse, and a frontier with free lanes is topped up from the stack.  The candidates
+// therefore come out exactly in the order of the one-row-at-a-time walk (DDL.sql:246-295 visited low first), and each
+// row is visited once.
+//
+// Three forms: COUNT (candidates per query), FILL (offsets known: ids, and source rows for verification, written in
+// place) and POOL = count and keep: the ids go to chunks of a device pool (64 slots: a link to the next chunk and 63
+// ids) taken with one atomic per chunk, so that one walk serves the two-call protocol -- k_search_gather then copies
+// each query's chunks to its CSR slice.  A query that finds the pool full is only counted (head -2) and walked again by
+// the FILL form.
+constexpr int SW_WARPS = 8;
+constexpr int SW_CHUNK = 64;
+constexpr int SW_CHUNK_IDS = SW_CHUNK - 1;
+constexpr u32 SW_LEAF = 0x80000000u;
+constexpr int SW_SPILL = 4096;  // per-warp global spill entries (pending rows <= 64 per tree level: 64 * 63 + 64)
+constexpr int SW_MODE_COUNT = 0, SW_MODE_POOL = 1, SW_MODE_FILL = 2;
+
+struct SwCtl  // device control block of one launch
+{
+  unsigned long long visits;
+  unsigned long long pool_cursor;
+  u32 work_cursor;
+  u32 err;  // bit 0: spill area exhausted, bit 1: some query found the pool full
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(SW_WARPS * 32)
+k_search_warp(const int4* __restrict__ node, const int* __restrict__ t_src, const float* __restrict__ queries, int dims,
+              int qpad, u32 nq, float prox, i64* __restrict__ offsets, i64* __restrict__ ids_out, int* __restrict__ src_out,
+              i64 cap, i64* __restrict__ pool, i64 pool_cap, i64* __restrict__ head, int only_unwritten,
+              u32* __restrict__ spill, int stack_cap, SwCtl* __restrict__ ctl)
+{
+  extern __shared__ u32 sw_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  u32* wbase = sw_smem + (size_t)warp * (qpad + 64 + stack_cap);
+  float* qs = reinterpret_cast<float*>(wbase);
+  u32* buf = wbase + qpad;   // [0, nf): the frontier; [0, 64): the new list of a round
+  u32* stack = buf + 64;
+  u32* gspill = spill + (size_t)(blockIdx.x * SW_WARPS + warp) * SW_SPILL;
+  const int H = stack_cap >> 1;
+  unsigned long long v = 0;
+  for (;;)
+  {
+    u32 qi = 0;
+    if (lane == 0) qi = atomicAdd(&ctl->work_cursor, 1u);
+    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if (qi >= nq) break;
+    if (MODE == SW_MODE_FILL && only_unwritten && head[qi] != -2) continue;
+    __syncwarp();
+    for (int d = lane; d < dims; d += 32) qs[d] = queries[(size_t)qi * dims + d];
+    if (lane == 0) buf[0] = 0u;  // RangeID 0
+    __syncwarp();
+    int nf = 1, sp = 0, gsp = 0;
+    i64 cnt = 0;
+    const i64 obase = MODE == SW_MODE_FILL ? offsets[qi] : 0;
+    i64 chunk = -1, prevc = -1, head_val = -1, chunk_no = -1;
+    bool dead = false;
+    for (;;)
+    {
+      if (sp == 0 && gsp > 0)
+      {
+        gsp -= H;
+        for (int i = lane; i < H; i += 32) stack[i] = __ldcg(gspill + gsp + i);
+        sp = H;
+        __syncwarp();
+      }
+      if (nf < 32 && sp > 0)
+      {
+        const int t = min(32 - nf, sp);
+        if (lane < t) buf[nf + lane] = stack[sp - 1 - lane];
+        sp -= t;
+        nf += t;
+        __syncwarp();
+      }
+      if (nf == 0) break;
+      const bool valid = lane < nf;
+      const u32 e = valid ? buf[lane] : 0u;
+      bool leaf = valid && (e & SW_LEAF) != 0u;
+      const u32 r = e & ~SW_LEAF;
+      const u32 m_unknown = __ballot_sync(0xffffffffu, valid && !leaf);
+      const int j0 = m_unknown ? __ffs(m_unknown) - 1 : nf;
+      int4 nd = make_int4(0, 0, 0, 0);
+      // rows not seen yet, and the flagged leaves that are certain to leave in this round (for their id)
+      const bool loaded = valid && (!leaf || lane < j0);
+      if (loaded) nd = __ldg(node + r);
+      if (valid && !leaf)
+      {
+        ++v;
+        leaf = nd.x < 0;
+      }
+      const u32 m_int = __ballot_sync(0xffffffffu, valid && !leaf);
+      const int j = m_int ? __ffs(m_int) - 1 : nf;  // entries [0, j) are leaves at the head of the list: final
+      // flagged leaves behind a row that has just turned out to be a leaf leave with it
+      if (valid && lane < j && !loaded) nd = __ldg(node + r);
+      if (j > 0)
+      {
+        if (MODE == SW_MODE_FILL)
+        {
+          if (lane < j && obase + cnt + lane < cap)
+          {
+            ids_out[obase + cnt + lane] = (i64)(((u64)(u32)nd.w << 32) | (u64)(u32)nd.z);
+            if (src_out) src_out[obase + cnt + lane] = t_src[r];
+          }
+        }
+        else if (MODE == SW_MODE_POOL)
+        {
+          if (!dead)
+          {
+            const i64 last_no = (cnt + j - 1) / SW_CHUNK_IDS;
+            if (last_no > chunk_no)
+            {
+              unsigned long long nw = 0;
+              if (lane == 0) nw = atomicAdd(&ctl->pool_cursor, (unsigned long long)SW_CHUNK);
+              nw = __shfl_sync(0xffffffffu, nw, 0);
+              if ((i64)nw + SW_CHUNK > pool_cap) dead = true;
+              else
+              {
+                if (lane == 0 && chunk >= 0) pool[chunk] = (i64)nw;
+                if (chunk < 0) head_val = (i64)nw;
+                prevc = chunk;
+                chunk = (i64)nw;
+                chunk_no = last_no;
+              }
+            }
+            if (!dead && lane < j)
+            {
+              const i64 p = cnt + lane;
+              const i64 no = p / SW_CHUNK_IDS;
+              const i64 c = no == chunk_no ? chunk : prevc;
+              pool[c + 1 + (p - no * SW_CHUNK_IDS)] = (i64)(((u64)(u32)nd.w << 32) | (u64)(u32)nd.z);
+            }
+          }
+        }
+        cnt += j;
+      }
+      bool gl = false, gh = false;
+      if (valid && !leaf)
+      {
+        const float x = qs[nd.x];
+        const float lo = __fsub_rn(x, prox);  // MinValue = value - @domain, DDL.sql:249
+        const float hi = __fadd_rn(x, prox);  // MaxValue = value + @domain, DDL.sql:250
+        const float mid = __int_as_float(nd.y);
+        gh = mid <= hi && nd.w >= 0;  // DDL.sql:280-293
+        gl = mid >= lo && nd.z >= 0;  // DDL.sql:265-278
+      }
+      const int c = (valid && lane >= j) ? (leaf ? 1 : (int)gl + (int)gh) : 0;
+      int incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const int pos = incl - c;
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      __syncwarp();  // every lane has read its frontier entry
+      if (c)
+      {
+        if (leaf) buf[pos] = r | SW_LEAF;
+        else
+        {
+          if (gl) buf[pos] = (u32)nd.z;
+          if (gh) buf[pos + (gl ? 1 : 0)] = (u32)nd.w;
+        }
+      }
+      __syncwarp();
+      nf = min(total, 32);
+      const int over = total - nf;
+      if (over > 0)
+      {
+        if (sp + over > stack_cap)
+        {
+          // shared stack full: its lower half goes to the warp's global area
+          if (gsp + H > SW_SPILL)
+          {
+            if (lane == 0) atomicOr(&ctl->err, 1u);
+            nf = 0;
+            sp = 0;
+            gsp = 0;
+            break;
+          }
+          for (int i = lane; i < H; i += 32) __stcg(gspill + gsp + i, stack[i]);
+          gsp += H;
+          const int rest = sp - H;
+          for (int b = 0; b < rest; b += 32)
+          {
+            const u32 t = (b + lane < rest) ? stack[H + b + lane] : 0u;
+            __syncwarp();
+            if (b + lane < rest) stack[b + lane] = t;
+            __syncwarp();
+          }
+          sp = rest;
+        }
+        if (lane < over) stack[sp + over - 1 - lane] = buf[32 + lane];  // reversed: the earliest ends on top
+        sp += over;
+        __syncwarp();
+      }
+    }
+    if (lane == 0)
+    {
+      if (MODE != SW_MODE_FILL) offsets[qi] = cnt;
+      if (MODE == SW_MODE_POOL)
+      {
+        head[qi] = dead ? -2 : head_val;
+        if (dead) atomicOr(&ctl->err, 2u);
+      }
+    }
+  }
+  if (MODE != SW_MODE_FILL)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && v) atomicAdd(&ctl->visits, v);
+  }
+}
+
+// POOL form, second half: one warp per query copies the query's chunks to its CSR slice
+__global__ void __launch_bounds__(256)
+k_search_gather(const i64* __restrict__ pool, const i64* __restrict__ head, const i64* __restrict__ offsets, u32 nq,
+                i64* __restrict__ ids_out, i64 cap)
+{
+  const int lane = threadIdx.x & 31;
+  const u32 nwarps = gridDim.x * 8u;
+  for (u32 q = blockIdx.x * 8u + (threadIdx.x >> 5); q < nq; q += nwarps)
+  {
+    i64 c = head[q];
+    if (c < 0) continue;  // no candidates, or not written (the FILL form walks that query again)
+    const i64 base = offsets[q], n = offsets[q + 1] - base;
+    for (i64 k = 0; k < n; k += SW_CHUNK_IDS)
+    {
+      const i64 m = min((i64)SW_CHUNK_IDS, n - k);
+      const i64 a = pool[c + lane];                             // slot 0 (lane 0): the link
+      const i64 b = (lane + 32 <= m) ? pool[c + lane + 32] : 0;  // slots 32..63
+      if (lane >= 1 && lane <= m && base + k + lane - 1 < cap) ids_out[base + k + lane - 1] = a;
+      if (lane + 32 <= m && base + k + lane + 31 < cap) ids_out[base + k + lane + 31] = b;
+      c = __shfl_sync(0xffffffffu, a, 0);
+    }
+  }
+}
+
+static int sw_grid(int64_t nq) { return (int)std::min<int64_t>((nq + SW_WARPS - 1) / SW_WARPS, (int64_t)VI_NUM_SMS * 8); }
+
+static u32 sw_env(const char* name, u32 def, u32 lo, u32 hi)
+{
+  const char* s = getenv(name);
+  if (!s || !*s) return def;
+  const long v = strtol(s, nullptr, 10);
+  return (u32)std::min<long>(std::max<long>(v, (long)lo), (long)hi);
+}
+
+template <typename T>
+static cudaError_t sw_ensure(T** p, int64_t* cap, int64_t need)
+{
+  if (*p && *cap >= need) return cudaSuccess;
+  cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  cudaError_t e = cudaMalloc((void**)p, (size_t)need * sizeof(T));
+  if (e == cudaSuccess) *cap = need;
+  return e;
+}
+
+// one launch of the warp kernel; ctl is zeroed first
+static int sw_launch(vi_ctx* ctx, int mode, const float* d_queries, int64_t nq, float prox, i64* d_offsets, i64* d_ids,
+                     int* d_src, int64_t cap, int only_unwritten)
+{
+  cudaStream_t st = ctx->stream;
+  const int grid = sw_grid(nq);
+  VI_CUDA_TRY(sw_ensure(&ctx->sw_spill, &ctx->sw_spill_cap, (int64_t)VI_NUM_SMS * 8 * SW_WARPS * SW_SPILL));
+  const int stack_cap = (int)sw_env("VI_B200_SEARCH_STACK", 256, 64, 2048) & ~63;
+  const int qpad = (ctx->dims + 31) & ~31;
+  const size_t smem = (size_t)SW_WARPS * (qpad + 64 + stack_cap) * sizeof(u32);
+  SwCtl* ctl = reinterpret_cast<SwCtl*>((unsigned long long*)ctx->counters + 8);
+  VI_CUDA_TRY(cudaMemsetAsync(ctl, 0, sizeof(SwCtl), st));
+#define SW_ARGS                                                                                                         \
+  ctx->t_node, ctx->t_src, d_queries, ctx->dims, qpad, (u32)nq, prox, d_offsets, d_ids, d_src, (i64)cap, ctx->sw_pool,     \
+      (i64)ctx->sw_pool_cap, ctx->sw_head, only_unwritten, ctx->sw_spill, stack_cap, ctl
+  if (mode == SW_MODE_COUNT)
+  {
+    VI_CUDA_TRY(cudaFuncSetAttribute(k_search_warp<SW_MODE_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_search_warp<SW_MODE_COUNT><<<grid, SW_WARPS * 32, smem, st>>>(SW_ARGS);
+  }
+  else if (mode == SW_MODE_POOL)
+  {
+    VI_CUDA_TRY(cudaFuncSetAttribute(k_search_warp<SW_MODE_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_search_warp<SW_MODE_POOL><<<grid, SW_WARPS * 32, smem, st>>>(SW_ARGS);
+  }
+  else
+  {
+    VI_CUDA_TRY(cudaFuncSetAttribute(k_search_warp<SW_MODE_FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_search_warp<SW_MODE_FILL><<<grid, SW_WARPS * 32, smem, st>>>(SW_ARGS);
+  }
+#undef SW_ARGS
+  return VI_OK;
+}
+
+static int sw_check(vi_ctx* ctx, const SwCtl& h)
+{
+  if (h.err & 1u) return ctx->fail(VI_ERR_STATE, "search: a warp's pending-row stack outgrew its spill area");
+  return VI_OK;
+}
+
 // have_offsets: d_offsets already holds the scanned counts of this very batch (skip the count pass)
+//
+// The count pass first walks a sample of the batch one thread per query; batches whose queries visit few rows (point
+// lookups) stay on that kernel, the others go to the warp-per-query kernel.  Unless the caller wants source rows
+// (ctx->search_want_src: verification, top-k), the warp count pass keeps the candidates in the pool, and the fill that
+// follows (here when d_ids is given, else the next call with have_offsets) is a copy instead of a second walk.
 int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proximity, i64* d_offsets, i64* d_ids,
                    int64_t cap, int64_t* total, int64_t* visits, bool have_offsets)
 {
   cudaStream_t st = ctx->stream;
   *total = 0;
   if (visits) *visits = 0;
+  if (!have_offsets) ctx->sw_pool_valid = false;
   if (nq == 0)
   {
     VI_CUDA_TRY(cudaMemsetAsync(d_offsets, 0, sizeof(i64), st));
@@ -135,16 +455,77 @@ int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proxim
     return VI_OK;
   }
   unsigned long long* d_vis = (unsigned long long*)ctx->counters + 1;  // counters[2..3]
+  SwCtl* d_ctl = reinterpret_cast<SwCtl*>((unsigned long long*)ctx->counters + 8);
   const u32 grid = (u32)((nq + 127) / 128);
   i64 tot = 0;
   unsigned long long vis = 0;
   if (!have_offsets)
   {
-    VI_CUDA_TRY(cudaMemsetAsync(d_vis, 0, 8, st));
-    k_search<false><<<grid, 128, 0, st>>>(ctx->t_node, ctx->t_src, d_queries, ctx->dims, (u32)nq, proximity, d_offsets,
-                                          nullptr, nullptr, 0, d_vis);
-    k_scan_i64<<<1, 1024, 0, st>>>(d_offsets, (u32)nq);
-    VI_CUDA_TRY(cudaMemcpyAsync(&vis, d_vis, 8, cudaMemcpyDeviceToHost, st));
+    // ---- which kernel: visits per query on a sample ------------------------------------------------------------
+    const u32 force = sw_env("VI_B200_SEARCH_PATH", 2, 0, 2);  // 0 thread, 1 warp, 2 by sample
+    int path = (int)force;
+    double cand_per_query = 0.0;
+    const int64_t ns = std::min<int64_t>(nq, 1024);
+    if (force == 2 || force == 1)
+    {
+      const u32 stride = (u32)(nq / ns);
+      VI_CUDA_TRY(cudaMemsetAsync(d_vis, 0, 8, st));
+      k_search<false><<<(u32)((ns + 127) / 128), 128, 0, st>>>(ctx->t_node, ctx->t_src, d_queries, ctx->dims, (u32)ns, stride,
+                                                               proximity, d_offsets, nullptr, nullptr, 0, d_vis);
+      k_scan_i64<<<1, 1024, 0, st>>>(d_offsets, (u32)ns);
+      i64 stot = 0;
+      VI_CUDA_TRY(cudaMemcpyAsync(&vis, d_vis, 8, cudaMemcpyDeviceToHost, st));
+      VI_CUDA_TRY(cudaMemcpyAsync(&stot, d_offsets + ns, sizeof(i64), cudaMemcpyDeviceToHost, st));
+      VI_CUDA_TRY(cudaStreamSynchronize(st));
+      cand_per_query = (double)stot / (double)ns;
+      if (force == 2) path = ((double)vis / (double)ns >= (double)sw_env("VI_B200_SEARCH_WARP_VISITS", 96, 1, 1u << 30)) ? 1 : 0;
+      vis = 0;
+    }
+    ctx->search_path = path;
+    if (path == 0)
+    {
+      VI_CUDA_TRY(cudaMemsetAsync(d_vis, 0, 8, st));
+      k_search<false><<<grid, 128, 0, st>>>(ctx->t_node, ctx->t_src, d_queries, ctx->dims, (u32)nq, 1u, proximity, d_offsets,
+                                            nullptr, nullptr, 0, d_vis);
+      k_scan_i64<<<1, 1024, 0, st>>>(d_offsets, (u32)nq);
+      VI_CUDA_TRY(cudaMemcpyAsync(&vis, d_vis, 8, cudaMemcpyDeviceToHost, st));
+    }
+    else
+    {
+      bool pool = !ctx->search_want_src && sw_env("VI_B200_SEARCH_POOL", 1, 0, 1) != 0;
+      if (pool)
+      {
+        // pool size from the sample: candidates per query + half a chunk of slack per query, 30 % head room
+        const double est = (cand_per_query * 1.3 * SW_CHUNK / SW_CHUNK_IDS + SW_CHUNK) * (double)nq + 65536.0;
+        int64_t need = (int64_t)std::min(est, 4.0e9);  // at most 32 GB; what does not fit is walked twice
+        const u32 cap_env = sw_env("VI_B200_SEARCH_POOL_SLOTS", 0, 0, 0x7fffffffu);
+        if (cap_env) need = cap_env;
+        if (sw_ensure(&ctx->sw_pool, &ctx->sw_pool_cap, need) != cudaSuccess ||
+            sw_ensure(&ctx->sw_head, &ctx->sw_head_cap, nq + 1) != cudaSuccess)
+        {
+          cudaGetLastError();
+          pool = false;
+        }
+      }
+      int rc = sw_launch(ctx, pool ? SW_MODE_POOL : SW_MODE_COUNT, d_queries, nq, proximity, d_offsets, nullptr, nullptr, 0, 0);
+      if (rc != VI_OK) return rc;
+      k_scan_i64<<<1, 1024, 0, st>>>(d_offsets, (u32)nq);
+      SwCtl h{};
+      VI_CUDA_TRY(cudaMemcpyAsync(&h, d_ctl, sizeof(SwCtl), cudaMemcpyDeviceToHost, st));
+      VI_CUDA_TRY(cudaMemcpyAsync(&tot, d_offsets + nq, sizeof(i64), cudaMemcpyDeviceToHost, st));
+      VI_CUDA_TRY(cudaStreamSynchronize(st));
+      if ((rc = sw_check(ctx, h)) != VI_OK) return rc;
+      vis = h.visits;
+      if (pool)
+      {
+        ctx->sw_pool_valid = true;
+        ctx->sw_pool_overflow = (h.err & 2u) != 0;
+        ctx->sw_q = d_queries;
+        ctx->sw_off = d_offsets;
+        ctx->sw_nq = nq;
+        ctx->sw_prox = proximity;
+      }
+    }
   }
   VI_CUDA_TRY(cudaMemcpyAsync(&tot, d_offsets + nq, sizeof(i64), cudaMemcpyDeviceToHost, st));
   VI_CUDA_TRY(cudaStreamSynchronize(st));
@@ -154,8 +535,26 @@ int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proxim
   if (cap < tot) return ctx->fail(VI_ERR_CAPACITY, "ids capacity smaller than the number of candidates");
   if (tot > 0)
   {
-    k_search<true><<<grid, 128, 0, st>>>(ctx->t_node, ctx->t_src, d_queries, ctx->dims, (u32)nq, proximity, d_offsets,
-                                         d_ids, ctx->search_src, cap, nullptr);
+    if (ctx->search_path == 0)
+      k_search<true><<<grid, 128, 0, st>>>(ctx->t_node, ctx->t_src, d_queries, ctx->dims, (u32)nq, 1u, proximity, d_offsets,
+                                           d_ids, ctx->search_src, cap, nullptr);
+    else
+    {
+      const bool from_pool = ctx->sw_pool_valid && ctx->search_src == nullptr && ctx->sw_q == d_queries &&
+                             ctx->sw_off == d_offsets && ctx->sw_nq == nq && ctx->sw_prox == proximity;
+      if (from_pool)
+        k_search_gather<<<(u32)std::min<int64_t>((nq + 7) / 8, (int64_t)VI_NUM_SMS * 16), 256, 0, st>>>(
+            ctx->sw_pool, ctx->sw_head, d_offsets, (u32)nq, d_ids, cap);
+      if (!from_pool || ctx->sw_pool_overflow)
+      {
+        int rc = sw_launch(ctx, SW_MODE_FILL, d_queries, nq, proximity, d_offsets, d_ids, ctx->search_src, cap, from_pool ? 1 : 0);
+        if (rc != VI_OK) return rc;
+        SwCtl h{};
+        VI_CUDA_TRY(cudaMemcpyAsync(&h, d_ctl, sizeof(SwCtl), cudaMemcpyDeviceToHost, st));
+        VI_CUDA_TRY(cudaStreamSynchronize(st));
+        if ((rc = sw_check(ctx, h)) != VI_OK) return rc;
+      }
+    }
     VI_CUDA_TRY(cudaStreamSynchronize(st));
   }
   VI_CUDA_TRY(cudaGetLastError());

@@ -10,15 +10,22 @@ struct StatsOut
 };
 
 // RangeValue { Dimension, Mid, Id } of a split range (IndexBuilder.cs:83-88) + the copy the partition pass reads
-__device__ __forceinline__ void write_split(const SegLevel& sg, const StatsOut& o, u32 s, int dim, float mid, i64 pivot)
+// The `mx` argument of the statistics kernels: bit 0 = this level takes the max-variance dimension; VI_MODE_SQL adds
+// bit 1 = a fallback range whose chosen Stdev2N is 0 gets a null Dimension / Mid (DDL.sql:193-194) and bit 2 = this is
+// dbo.BuildIndex's root, which sends Value = Mean to the high child whatever the id (DDL.sql:104).
+constexpr int VI_MX_MAX = 1, VI_MX_SQL = 2, VI_MX_ROOT_HIGH = 4;
+
+__device__ __forceinline__ void write_split(const SegLevel& sg, const StatsOut& o, u32 s, int dim, float mid, i64 pivot,
+                                            bool null_dim = false, bool root_high = false)
 {
   const u32 row = sg.row[s];
-  o.t_dim[row] = dim;
-  o.t_mid[row] = mid;
+  o.t_dim[row] = null_dim ? VI_DIM_NULL : dim;
+  o.t_mid[row] = null_dim ? __int_as_float(0x7fc00000) : mid;
   o.t_id[row] = pivot;
+  // the partition pass always splits on (dim, mid, pivot): with Stdev = 0 every value equals mid and the ids decide
   sg.dim[s] = dim;
   sg.mid[s] = mid;
-  sg.pivot[s] = pivot;
+  sg.pivot[s] = (root_high && !null_dim) ? (i64)INT64_MIN : pivot;  // id > INT64_MIN: ties go high
 }
 
 // (long)(IdN / Count), Int128 division truncating toward zero (IndexBuilder.cs:87).

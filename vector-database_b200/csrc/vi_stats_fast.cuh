@@ -113,7 +113,8 @@ template <int TS, int CH, bool FULL, bool WPS>
 __global__ void __launch_bounds__(256, (CH == 1) ? 4 : ((TS * CH <= 32) ? 3 : 1))
 k_stats_small_fast(const LevelDev* __restrict__ lvp, SegLevel sg, u32 nmin, u32 nmax, const u32* __restrict__ perm,
                    const i64* __restrict__ pid, const float* __restrict__ rows, int ld, int dims, float qk, double qinv, int mx,
-                   StatsOut out)
+                   StatsOut out, u64* __restrict__ gacc, const u32* __restrict__ bl_parent, const u32* __restrict__ bl_sib,
+                   u32 keep_thr)
 {
   const u32 R = lvp->R;
   constexpr int NTW = 32 / TS;            // teams per warp
@@ -133,6 +134,12 @@ k_stats_small_fast(const LevelDev* __restrict__ lvp, SegLevel sg, u32 nmin, u32 
     n = sg.count[s];
     S = sg.start[s];
     if (n < nmin || n >= nmax) n = 0;
+    if (WPS && n != 0 && gacc != nullptr)
+    {
+      // a range with a big-list slot whose sums are derived (parent - sibling) is k_finalize_big_fast's
+      const u32 slot = sg.bslot[s];
+      if (slot != 0xffffffffu && bl_parent[slot] != 0xffffffffu) n = 0;
+    }
   }
   if (n == 0) return;  // n is uniform over the group
   const int C4 = FULL ? TS * CH : (ld >> 2);
@@ -191,6 +198,35 @@ k_stats_small_fast(const LevelDev* __restrict__ lvp, SegLevel sg, u32 nmin, u32 
           s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
         }
     }
+    // A summed range with a big-list slot keeps its sums if its own children may form a pair or its sibling is derived
+    // from them (looked up here, after the row loop, so that nothing of it is live across the loop):
+    // [dim][S1, S2 low 32 bits, S2 >> 32], the layout k_finalize_big_fast derives from
+    u64* g = nullptr;
+    if (WPS && gacc != nullptr && trow == 0)
+    {
+      const u32 slot = sg.bslot[s];
+      if (slot != 0xffffffffu && (n >= keep_thr || bl_sib[slot] != 0xffffffffu))
+        g = gacc + (size_t)slot * ((size_t)ld * 3 + 3);
+    }
+    if (WPS && g != nullptr)
+    {
+#pragma unroll
+      for (int k = 0; k < CH; ++k)
+      {
+        const int c = c0 + k * TS + tl;
+        if (FULL || c < C4)
+        {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+          {
+            u64* gd = g + (size_t)(c * 4 + e) * 3;
+            gd[0] = (u64)s1[k * 4 + e];
+            gd[1] = s2[k * 4 + e] & 0xffffffffull;
+            gd[2] = s2[k * 4 + e] >> 32;
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < CH; ++k)
 #pragma unroll
@@ -200,7 +236,7 @@ k_stats_small_fast(const LevelDev* __restrict__ lvp, SegLevel sg, u32 nmin, u32 
         if (d < dims)
         {
           const Key128 key = qfx_key(n, s1[k * 4 + e], s2[k * 4 + e], 0ull);
-          if (qfx_better(mx != 0, key, d, best.key, best.idx))
+          if (qfx_better((mx & VI_MX_MAX) != 0, key, d, best.key, best.idx))
           {
             best.key = key;
             best.s1 = s1[k * 4 + e];
@@ -209,14 +245,16 @@ k_stats_small_fast(const LevelDev* __restrict__ lvp, SegLevel sg, u32 nmin, u32 
         }
       }
   }
-  best = qfx_reduce<TS>(best, mx != 0, tmask);
+  best = qfx_reduce<TS>(best, (mx & VI_MX_MAX) != 0, tmask);
   int dim = best.idx;
   float mid = qfx_mid(best.s1, n, qinv);
+  bool null_dim = false;
   if (key_lt(best.key, thr))  // the chosen dimension is poorly resolved (uniform over the team after the reduction)
   {
-    const ExBest eb = welford_team<TS, CH>(rows, ld, dims, pp, n, tl, tmask, mx != 0);
+    const ExBest eb = welford_team<TS, CH>(rows, ld, dims, pp, n, tl, tmask, (mx & VI_MX_MAX) != 0);
     dim = eb.idx;
     mid = eb.mean;
+    null_dim = (mx & VI_MX_SQL) != 0 && eb.key == 0.f;  // Stdev = 0 (DDL.sql:193-194)
   }
   // id sum (Stats.IdN): 32-bit halves in two 64-bit accumulators hold the Int128 sum exactly
   u64 slo = (u32)id0;
@@ -233,7 +271,23 @@ k_stats_small_fast(const LevelDev* __restrict__ lvp, SegLevel sg, u32 nmin, u32 
     slo += __shfl_xor_sync(gmask, slo, o);
     shi += __shfl_xor_sync(gmask, shi, o);
   }
-  if (gl == 0) write_split(sg, out, s, dim, mid, mean_id(slo, shi, n));
+  if (gl == 0)
+  {
+    write_split(sg, out, s, dim, mid, mean_id(slo, shi, n), null_dim, (mx & VI_MX_ROOT_HIGH) != 0);
+    u64* g = nullptr;
+    if (WPS && gacc != nullptr)
+    {
+      const u32 slot = sg.bslot[s];
+      if (slot != 0xffffffffu && (n >= keep_thr || bl_sib[slot] != 0xffffffffu))
+        g = gacc + (size_t)slot * ((size_t)ld * 3 + 3);
+    }
+    if (WPS && g != nullptr)
+    {
+      g[(size_t)ld * 3 + 0] = slo;
+      g[(size_t)ld * 3 + 1] = (u64)shi;
+      g[(size_t)ld * 3 + 2] = (u64)n;
+    }
+  }
 }
 
 // Arg-max over the combined sums of one big range, by one warp.  acc: [dim][S1, S2 limb0, S2 limb1] (shared or
@@ -257,16 +311,17 @@ __device__ __forceinline__ void finalize_big_range(const SegLevel& sg, u32 s, u3
     const u64 s2lo = l0 + (l1 << 32);
     const u64 s2hi = (l1 >> 32) + ((s2lo < l0) ? 1ull : 0ull);
     const Key128 key = qfx_key(n, s1, s2lo, s2hi);
-    if (qfx_better(mx != 0, key, d, best.key, best.idx))
+    if (qfx_better((mx & VI_MX_MAX) != 0, key, d, best.key, best.idx))
     {
       best.key = key;
       best.s1 = s1;
       best.idx = d;
     }
   }
-  best = qfx_reduce<32>(best, mx != 0, 0xffffffffu);
+  best = qfx_reduce<32>(best, (mx & VI_MX_MAX) != 0, 0xffffffffu);
   int dim = best.idx;
   float mid = qfx_mid(best.s1, n, qinv);
+  bool null_dim = false;
   if (key_lt(best.key, thr))  // the chosen dimension is poorly resolved
   {
     if (no_fallback_err)
@@ -275,11 +330,13 @@ __device__ __forceinline__ void finalize_big_range(const SegLevel& sg, u32 s, u3
       return;
     }
     // many points that the quantisation cannot tell apart: reference arithmetic, one warp (rare, slow)
-    const ExBest eb = welford_team<32, 1>(rows, ld, dims, perm + sg.start[s], n, lane, 0xffffffffu, mx != 0);
+    const ExBest eb = welford_team<32, 1>(rows, ld, dims, perm + sg.start[s], n, lane, 0xffffffffu, (mx & VI_MX_MAX) != 0);
     dim = eb.idx;
     mid = eb.mean;
+    null_dim = (mx & VI_MX_SQL) != 0 && eb.key == 0.f;  // Stdev = 0 (DDL.sql:193-194)
   }
-  if (lane == 0) write_split(sg, out, s, dim, mid, mean_id(ids[0], (i64)ids[1], n));
+  if (lane == 0)
+    write_split(sg, out, s, dim, mid, mean_id(ids[0], (i64)ids[1], n), null_dim, (mx & VI_MX_ROOT_HIGH) != 0);
 }
 
 // One CTA owns one chunk (VI_CHUNK rows) of one big range.  A range that fits one chunk (and one column pass) is
@@ -467,7 +524,7 @@ __global__ void __launch_bounds__(256)
 k_finalize_big_fast(const LevelDev* __restrict__ lvp, SegLevel sg, const u32* __restrict__ big_list, u64* __restrict__ gacc,
                     const u64* __restrict__ gacc_prev, int ld, int dims, double qinv, int mx, StatsOut out,
                     const float* __restrict__ rows, const u32* __restrict__ perm, int single_pass, int shared,
-                    u32* __restrict__ err, const u32* __restrict__ bl_parent, const u32* __restrict__ bl_sib)
+                    u32* __restrict__ err, const u32* __restrict__ bl_parent, const u32* __restrict__ bl_sib, u32 t_big)
 {
   const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -498,6 +555,7 @@ k_finalize_big_fast(const LevelDev* __restrict__ lvp, SegLevel sg, const u32* __
   // shared phase of a multi-rank build: n is the all-reduced (global) count and the float32 fallback, which needs
   // the range's rows in global order, is not available: a poorly resolved range is reported as an error
   const u32 n = shared ? (u32)g[(size_t)ld * 3 + 2] : sg.count[s];
+  if (!shared && !derived && n < t_big) return;                     // finished by the warp-per-range kernel
   if (!shared && single_pass && n <= VI_CHUNK && !derived) return;  // finished by its chunk CTA
   finalize_big_range(sg, s, n, g, g + (size_t)ld * 3, ld, dims, qinv, mx, out, rows, perm, lane, shared ? err : nullptr);
 }

@@ -99,7 +99,9 @@ int vi_search_topk_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float p
   int64_t cand = 0;
   int* keep_src = ctx->search_src;
   ctx->search_src = nullptr;
+  ctx->search_want_src = true;  // the fill pass records source rows: count only, no candidate pool
   int rc = vi_search_impl(ctx, d_queries, nq, proximity, ctx->off_buf, nullptr, 0, &cand, nullptr, false);
+  ctx->search_want_src = false;
   ctx->search_src = keep_src;
   if (rc != VI_OK) return rc;
   if (cand >= (int64_t)0x7fffffff) return ctx->fail(VI_ERR_CAPACITY, "too many candidates for one top-k call: split the batch");
