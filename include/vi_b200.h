@@ -109,6 +109,25 @@ int vi_points_add_device(vi_ctx* ctx, const int64_t* d_ids, const float* d_rows,
 int vi_points_add_records(vi_ctx* ctx, const void* records, int64_t n, int32_t dims);
 int vi_points_add_file(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, int32_t dims, double* read_ms,
                        double* total_ms);
+/* The reference's test program takes its real data set from an ANN-benchmarks HDF5 file: GetHdf5DatasetSize reads the
+ * 2-D extent of `/train`, GetHdf5Dataset yields (row index, float[dimension]) in blocks of 100000 rows
+ * (VectorIndex.MainTest/Program.cs:183-260, through HDF5-CSharp = libhdf5).  A minimal native reader of the container
+ * (csrc/vi_hdf5.cu: superblock 0-3, symbol-table or compact-link groups, object headers 1 / 2, CONTIGUOUS unfiltered
+ * little-endian data sets of rank 1 or 2; anything else is refused with a message):
+ *   vi_hdf5_dataset_info  extent and element type of `dataset` ("/train", "test", "a/b"), and where its bytes start;
+ *                         rank other than 1 or 2 -> VI_ERR_INVALID_ARG "Invalid rank." (Program.cs:203-206); ctx may be
+ *                         NULL (no error text then);
+ *   vi_hdf5_read_rows     rows [first_row, first_row + n) into a host buffer (the `/test` queries, `/neighbors`);
+ *   vi_points_add_hdf5    appends float32 rows [first_row, first_row + n) (n < 0: to the end) with ids first_id,
+ *                         first_id + 1, ... (Program.cs:252 yields the row index) through the pinned double-buffered
+ *                         pipeline of vi_points_add_file: reading one batch overlaps the H2D copy of the one before. */
+int vi_hdf5_dataset_info(vi_ctx* ctx, const char* path, const char* dataset, int64_t* rows, int64_t* cols,
+                         int32_t* elem_class /* 0 integer, 1 IEEE float */, int32_t* elem_bytes, int64_t* data_offset);
+const char* vi_hdf5_last_error(void); /* text of the calling thread's last failed vi_hdf5_* call made with ctx == NULL */
+int vi_hdf5_read_rows(vi_ctx* ctx, const char* path, const char* dataset, int64_t first_row, int64_t n, void* out,
+                      int64_t out_bytes);
+int vi_points_add_hdf5(vi_ctx* ctx, const char* path, const char* dataset, int64_t first_row, int64_t n, int64_t first_id,
+                       double* read_ms, double* total_ms);
 int64_t vi_points_count(const vi_ctx* ctx);
 
 /* ---- build: IndexBuilder.Build (IndexBuilder.cs:23-157) ------------------------------------------------------ */

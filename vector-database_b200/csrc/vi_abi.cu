@@ -225,10 +225,11 @@ int64_t vi_points_count(const vi_ctx* ctx) { return ctx ? ctx->n : 0; }
 int vi_build(vi_ctx* ctx, int32_t mode, vi_build_info* info)
 {
   if (!ctx) return VI_ERR_INVALID_ARG;
-  if (mode != VI_MODE_EXACT && mode != VI_MODE_FAST) return ctx->fail(VI_ERR_INVALID_ARG, "unknown build mode");
+  if (mode != VI_MODE_EXACT && mode != VI_MODE_FAST && mode != VI_MODE_SQL)
+    return ctx->fail(VI_ERR_INVALID_ARG, "unknown build mode");
   if (ctx->dims == 0) return ctx->fail(VI_ERR_STATE, "no points: vi_points_reserve / vi_points_add first");
-  if (ctx->world > 1 && mode != VI_MODE_FAST)
-    return ctx->fail(VI_ERR_INVALID_ARG, "multi-rank build needs VI_MODE_FAST (order-independent sums)");
+  if (ctx->world > 1 && mode == VI_MODE_EXACT)
+    return ctx->fail(VI_ERR_INVALID_ARG, "multi-rank build needs VI_MODE_FAST or VI_MODE_SQL (order-independent sums)");
   VI_CUDA_TRY(cudaSetDevice(ctx->device));
   ctx->pending_nq = -1;
   int rc = vi_build_impl(ctx, mode);
@@ -300,14 +301,18 @@ int vi_textindex_copy(const vi_ctx* cctx, int64_t* range_id, int16_t* dimension,
   if (rc != VI_OK) return rc;
   VI_CUDA_TRY(cudaMemcpy(lo.data(), ctx->t_low, (size_t)k * 4, cudaMemcpyDeviceToHost));
   VI_CUDA_TRY(cudaMemcpy(hi.data(), ctx->t_high, (size_t)k * 4, cudaMemcpyDeviceToHost));
+  // a table built by VI_MODE_SQL names both children of every range of more than one point, present or not, as
+  // dbo.BuildIndex does (DDL.sql:195-196 `iif(Count = 1, null, RangeID * 2 + 1)`)
+  const bool sql = ctx->info.mode == VI_MODE_SQL;
   for (int64_t i = 0; i < k; ++i)
   {
-    const bool leaf = dim[i] < 0;
+    const bool leaf = dim[i] == -1;
+    const bool null_dim = dim[i] < 0;  // leaves and Stdev = 0 rows (VI_DIM_NULL): DDL.sql:193-194
     if (range_id) range_id[i] = rid[i];
-    if (dimension) dimension[i] = leaf ? (int16_t)-1 : (int16_t)dim[i];
-    if (mid) mid[i] = leaf ? NAN : m[i];
-    if (low_range_id) low_range_id[i] = lo[i] >= 0 ? rid[lo[i]] : -1;
-    if (high_range_id) high_range_id[i] = hi[i] >= 0 ? rid[hi[i]] : -1;
+    if (dimension) dimension[i] = null_dim ? (int16_t)-1 : (int16_t)dim[i];
+    if (mid) mid[i] = null_dim ? NAN : m[i];
+    if (low_range_id) low_range_id[i] = (sql && !leaf) ? rid[i] * 2 + 1 : (lo[i] >= 0 ? rid[lo[i]] : -1);
+    if (high_range_id) high_range_id[i] = (sql && !leaf) ? rid[i] * 2 + 2 : (hi[i] >= 0 ? rid[hi[i]] : -1);
     if (text_id) text_id[i] = leaf ? id[i] : -1;  // DDL.sql:195-197: internal rows carry no TextID
   }
   return VI_OK;

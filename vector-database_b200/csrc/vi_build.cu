@@ -340,7 +340,8 @@ int vi_debug_divcheck_impl(vi_ctx* ctx, uint64_t seed, int64_t samples, int64_t*
 // =============================================================================================================
 struct BuildEnv
 {
-  int mode;
+  int mode;     // statistics: VI_MODE_EXACT or VI_MODE_FAST (VI_MODE_SQL builds with the fast mode's kernels and sql = 1)
+  int sql;      // dbo.BuildIndex's rules (DDL.sql:44-202): level_mx()
   u32 t_team, t_big, big_unroll;
   u32 t_slot;   // ranges of >= t_slot points get a big-list slot (their sums can be kept / derived); t_slot <= t_big
   u32 sibling;  // fast mode: sum only the smaller child of a big pair, derive the other from the parent (1 = on)
@@ -383,8 +384,19 @@ static void env_cleanup(BuildEnv& env)
   env.ev.clear();
 }
 
+// the `mx` argument of a level's statistics kernels (vi_stats_common.cuh): IndexBuilder alternates max / min from the
+// root (IndexBuilder.cs:33,128-129); dbo.BuildIndex takes the minimum at depth 1 only (DDL.sql:113,151,155) and its
+// root sends ties high (DDL.sql:104)
+static int level_mx(const BuildEnv& env, int level)
+{
+  if (!env.sql) return (level & 1) == 0 ? VI_MX_MAX : 0;
+  return (level != 1 ? VI_MX_MAX : 0) | VI_MX_SQL | (level == 0 ? VI_MX_ROOT_HIGH : 0);
+}
+
 static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
 {
+  env.sql = mode == VI_MODE_SQL ? 1 : 0;
+  if (env.sql) mode = VI_MODE_FAST;
   env.mode = mode;
   // range-size classes (see vi_stats_fast.cuh / vi_stats_exact.cuh); defaults from scripts/sweep.py on 10M x 96
   // (profiles/r1_sweep.txt); the variables exist for such sweeps
@@ -507,7 +519,7 @@ static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* 
     k_subtree_fast<CH, FULL><<<grid, SUB_WARPS * 32, smem, st>>>(sl, s.sub_cnt, ctx->sub_perm, ctx->sub_pid, rows, ld, dims, \
                                                                  env.qk, env.qinv, tout, ctx->t_src, row_base,            \
                                                                  overflow_base, (u32)ctx->t_cap, cnt, lvlp, lvlr,         \
-                                                                 rows_max);                                               \
+                                                                 rows_max, env.sql);                                      \
   } while (0)
   const int ch = std::min(4, (ld / 4 + 7) / 8);  // int4 columns per team lane and pass
   const bool sub_full = ld == 32 * ch && dims == ld;
@@ -602,7 +614,7 @@ static int enqueue_level(vi_ctx* ctx, BuildEnv& env, const LevelState& b, int le
   const int ld = ctx->ld, dims = ctx->dims;
   const int mode = env.mode;
   const int nxt = cur ^ 1;
-  const int mx = (level & 1) == 0;  // root max = true, children !max (IndexBuilder.cs:33,128-129)
+  const int mx = level_mx(env, level);
   SegLevel& sg = ctx->seg[cur];
   TableOut tout{ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high};
   StatsOut sout{ctx->t_dim, ctx->t_mid, ctx->t_id};
@@ -1068,7 +1080,7 @@ static int build_sharded_try(vi_ctx* ctx, BuildEnv& env, int Lcap, int* retry_le
   {
     if (level >= VI_MAX_DEPTH) return ctx->fail(VI_ERR_OVERFLOW, "rangeId overflow (IndexBuilder.cs:99)");
     const int cur = level & 1, nxt = cur ^ 1;
-    const int mx = (level & 1) == 0;
+    const int mx = level_mx(env, level);
     const u32 Rb = (u32)std::min(1 << level, VI_SH_MAXR);  // bound on the level's ranges
     SegLevel& sg = ctx->seg[cur];
     LevelDev* lvp = ctx->lv + level;

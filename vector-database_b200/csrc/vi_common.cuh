@@ -20,6 +20,8 @@ constexpr u32 VI_MIN_BIG = 64;   // smallest allowed "big range" threshold (size
 // Rows of a big range handled by one CTA of the fast-mode statistics kernel.
 constexpr u32 VI_CHUNK = 4096;
 constexpr int VI_NUM_SMS = 148;
+// packed traversal row: x = Dimension, or < 0 for a leaf, or VI_NODE_BOTH for an internal row with Dimension = null
+constexpr int VI_NODE_BOTH = 0x7fffffff;
 constexpr int VI_MAX_DEPTH = 62;  // IndexBuilder.cs:99,104: splitting a depth-62 range overflows rangeId
 
 #define VI_CUDA_TRY(expr)                                                                 \

@@ -593,9 +593,9 @@ __global__ void k_pack_nodes(const int* __restrict__ t_dim, const float* __restr
   if (i >= n) return;
   const int d = t_dim[i];
   int4 v;
-  v.x = d;
+  v.x = d == VI_DIM_NULL ? VI_NODE_BOTH : d;  // Dimension = null (VI_MODE_SQL): the walk follows both children
   v.y = __float_as_int(t_mid[i]);
-  if (d < 0)
+  if (d < 0 && d != VI_DIM_NULL)
   {
     const u64 id = (u64)t_id[i];  // leaf: carry the TextID in the child slots
     v.z = (int)(u32)id;

@@ -103,12 +103,13 @@ k_search(const int4* __restrict__ node, const int* __restrict__ t_src, const flo
         ++cnt;
         continue;
       }
-      const float x = __ldg(q + nd.x);
+      const bool both = nd.x == VI_NODE_BOTH;  // `N.Dimension is null or ...` DDL.sql:275,290
+      const float x = both ? 0.f : __ldg(q + nd.x);
       const float lo = __fsub_rn(x, prox);  // MinValue = value - @domain, DDL.sql:249
       const float hi = __fadd_rn(x, prox);  // MaxValue = value + @domain, DDL.sql:250
       const float mid = __int_as_float(nd.y);
-      if (mid <= hi && nd.w >= 0) stack[sp++] = (u32)nd.w;  // DDL.sql:280-293 (pushed first, visited second)
-      if (mid >= lo && nd.z >= 0) stack[sp++] = (u32)nd.z;  // DDL.sql:265-278
+      if ((both || mid <= hi) && nd.w >= 0) stack[sp++] = (u32)nd.w;  // DDL.sql:280-293 (pushed first, visited second)
+      if ((both || mid >= lo) && nd.z >= 0) stack[sp++] = (u32)nd.z;  // DDL.sql:265-278
     }
     if (!FILL) offsets[i] = cnt;
   }
@@ -155,9 +156,9 @@ struct SwCtl  // device control block of one launch
 template <int MODE>
 __global__ void __launch_bounds__(SW_WARPS * 32)
 k_search_warp(const int4* __restrict__ node, const int* __restrict__ t_src, const float* __restrict__ queries, int dims,
-              int qpad, u32 nq, float prox, i64* __restrict__ offsets, i64* __restrict__ ids_out, int* __restrict__ src_out,
-              i64 cap, i64* __restrict__ pool, i64 pool_cap, i64* __restrict__ head, int only_unwritten,
-              u32* __restrict__ spill, int stack_cap, SwCtl* __restrict__ ctl)
+              int qpad, u32 nq, u32 stride, float prox, i64* __restrict__ offsets, i64* __restrict__ ids_out,
+              int* __restrict__ src_out, i64 cap, i64* __restrict__ pool, u32 pool_cap, i64* __restrict__ head,
+              int only_unwritten, u32* __restrict__ spill, int stack_cap, SwCtl* __restrict__ ctl)
 {
   extern __shared__ u32 sw_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -176,13 +177,16 @@ k_search_warp(const int4* __restrict__ node, const int* __restrict__ t_src, cons
     if (qi >= nq) break;
     if (MODE == SW_MODE_FILL && only_unwritten && head[qi] != -2) continue;
     __syncwarp();
-    for (int d = lane; d < dims; d += 32) qs[d] = queries[(size_t)qi * dims + d];
+    for (int d = lane; d < dims; d += 32) qs[d] = queries[(size_t)qi * stride * dims + d];
     if (lane == 0) buf[0] = 0u;  // RangeID 0
     __syncwarp();
     int nf = 1, sp = 0, gsp = 0;
-    i64 cnt = 0;
+    u32 cnt = 0;  // candidates so far (a table has fewer than 2^31 rows)
     const i64 obase = MODE == SW_MODE_FILL ? offsets[qi] : 0;
-    i64 chunk = -1, prevc = -1, head_val = -1, chunk_no = -1;
+    // POOL: the chunk being filled (slot index of its link word), the one before it, the first one, and the number of
+    // ids already in the current chunk
+    u32 chunk = 0xffffffffu, prevc = 0xffffffffu, head_val = 0xffffffffu;
+    int fill = SW_CHUNK_IDS;  // "full": the first emission takes a chunk
     bool dead = false;
     for (;;)
     {
@@ -225,63 +229,67 @@ k_search_warp(const int4* __restrict__ node, const int* __restrict__ t_src, cons
       {
         if (MODE == SW_MODE_FILL)
         {
-          if (lane < j && obase + cnt + lane < cap)
+          const i64 o = obase + (i64)cnt + lane;
+          if (lane < j && o < cap)
           {
-            ids_out[obase + cnt + lane] = (i64)(((u64)(u32)nd.w << 32) | (u64)(u32)nd.z);
-            if (src_out) src_out[obase + cnt + lane] = t_src[r];
+            ids_out[o] = (i64)(((u64)(u32)nd.w << 32) | (u64)(u32)nd.z);
+            if (src_out) src_out[o] = t_src[r];
           }
         }
         else if (MODE == SW_MODE_POOL)
         {
           if (!dead)
           {
-            const i64 last_no = (cnt + j - 1) / SW_CHUNK_IDS;
-            if (last_no > chunk_no)
+            // lanes [0, room) still fit the current chunk, the others open the next one (j <= 32 < 63: at most one)
+            const int room = SW_CHUNK_IDS - fill;
+            if (j > room)
             {
               unsigned long long nw = 0;
               if (lane == 0) nw = atomicAdd(&ctl->pool_cursor, (unsigned long long)SW_CHUNK);
               nw = __shfl_sync(0xffffffffu, nw, 0);
-              if ((i64)nw + SW_CHUNK > pool_cap) dead = true;
+              if (nw + SW_CHUNK > (unsigned long long)pool_cap) dead = true;
               else
               {
-                if (lane == 0 && chunk >= 0) pool[chunk] = (i64)nw;
-                if (chunk < 0) head_val = (i64)nw;
+                if (lane == 0 && chunk != 0xffffffffu) pool[chunk] = (i64)nw;
+                if (chunk == 0xffffffffu) head_val = (u32)nw;
                 prevc = chunk;
-                chunk = (i64)nw;
-                chunk_no = last_no;
+                chunk = (u32)nw;
               }
             }
-            if (!dead && lane < j)
+            if (!dead)
             {
-              const i64 p = cnt + lane;
-              const i64 no = p / SW_CHUNK_IDS;
-              const i64 c = no == chunk_no ? chunk : prevc;
-              pool[c + 1 + (p - no * SW_CHUNK_IDS)] = (i64)(((u64)(u32)nd.w << 32) | (u64)(u32)nd.z);
+              if (lane < j)
+              {
+                const u32 slot = lane < room ? (j > room ? prevc : chunk) + 1u + (u32)(fill + lane)
+                                             : chunk + 1u + (u32)(lane - room);
+                pool[slot] = (i64)(((u64)(u32)nd.w << 32) | (u64)(u32)nd.z);
+              }
+              fill = j > room ? j - room : fill + j;
             }
           }
         }
-        cnt += j;
+        cnt += (u32)j;
       }
       bool gl = false, gh = false;
       if (valid && !leaf)
       {
-        const float x = qs[nd.x];
+        const bool both = nd.x == VI_NODE_BOTH;  // `N.Dimension is null or ...` DDL.sql:275,290
+        const float x = both ? 0.f : qs[nd.x];
         const float lo = __fsub_rn(x, prox);  // MinValue = value - @domain, DDL.sql:249
         const float hi = __fadd_rn(x, prox);  // MaxValue = value + @domain, DDL.sql:250
         const float mid = __int_as_float(nd.y);
-        gh = mid <= hi && nd.w >= 0;  // DDL.sql:280-293
-        gl = mid >= lo && nd.z >= 0;  // DDL.sql:265-278
+        gh = (both || mid <= hi) && nd.w >= 0;  // DDL.sql:280-293
+        gl = (both || mid >= lo) && nd.z >= 0;  // DDL.sql:265-278
       }
-      const int c = (valid && lane >= j) ? (leaf ? 1 : (int)gl + (int)gh) : 0;
-      int incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
-      {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      const int pos = incl - c;
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      // new list position of this lane's entries: leaves behind j keep one slot, rows expand to 0, 1 or 2
+      const bool keep = valid && lane >= j;
+      const bool one = keep && (leaf || gl || gh);
+      const bool two = keep && !leaf && gl && gh;
+      const int c = (int)one + (int)two;
+      const u32 m1 = __ballot_sync(0xffffffffu, one), m2 = __ballot_sync(0xffffffffu, two);
+      const u32 below = (1u << lane) - 1u;
+      const int pos = __popc(m1 & below) + __popc(m2 & below);
+      const int total = __popc(m1) + __popc(m2);
       __syncwarp();  // every lane has read its frontier entry
       if (c)
       {
@@ -327,10 +335,10 @@ k_search_warp(const int4* __restrict__ node, const int* __restrict__ t_src, cons
     }
     if (lane == 0)
     {
-      if (MODE != SW_MODE_FILL) offsets[qi] = cnt;
+      if (MODE != SW_MODE_FILL) offsets[qi] = (i64)cnt;
       if (MODE == SW_MODE_POOL)
       {
-        head[qi] = dead ? -2 : head_val;
+        head[qi] = dead ? -2 : (head_val == 0xffffffffu ? -1 : (i64)head_val);
         if (dead) atomicOr(&ctl->err, 2u);
       }
     }
@@ -390,8 +398,8 @@ static cudaError_t sw_ensure(T** p, int64_t* cap, int64_t need)
 }
 
 // one launch of the warp kernel; ctl is zeroed first
-static int sw_launch(vi_ctx* ctx, int mode, const float* d_queries, int64_t nq, float prox, i64* d_offsets, i64* d_ids,
-                     int* d_src, int64_t cap, int only_unwritten)
+static int sw_launch(vi_ctx* ctx, int mode, const float* d_queries, int64_t nq, u32 stride, float prox, i64* d_offsets,
+                     i64* d_ids, int* d_src, int64_t cap, int only_unwritten)
 {
   cudaStream_t st = ctx->stream;
   const int grid = sw_grid(nq);
@@ -402,8 +410,9 @@ static int sw_launch(vi_ctx* ctx, int mode, const float* d_queries, int64_t nq, 
   SwCtl* ctl = reinterpret_cast<SwCtl*>((unsigned long long*)ctx->counters + 8);
   VI_CUDA_TRY(cudaMemsetAsync(ctl, 0, sizeof(SwCtl), st));
 #define SW_ARGS                                                                                                         \
-  ctx->t_node, ctx->t_src, d_queries, ctx->dims, qpad, (u32)nq, prox, d_offsets, d_ids, d_src, (i64)cap, ctx->sw_pool,     \
-      (i64)ctx->sw_pool_cap, ctx->sw_head, only_unwritten, ctx->sw_spill, stack_cap, ctl
+  ctx->t_node, ctx->t_src, d_queries, ctx->dims, qpad, (u32)nq, stride, prox, d_offsets, d_ids, d_src, (i64)cap,           \
+      ctx->sw_pool, (u32)std::min<int64_t>(ctx->sw_pool_cap, 0xffffff00ll), ctx->sw_head, only_unwritten, ctx->sw_spill,  \
+      stack_cap, ctl
   if (mode == SW_MODE_COUNT)
   {
     VI_CUDA_TRY(cudaFuncSetAttribute(k_search_warp<SW_MODE_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -465,21 +474,23 @@ int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proxim
     const u32 force = sw_env("VI_B200_SEARCH_PATH", 2, 0, 2);  // 0 thread, 1 warp, 2 by sample
     int path = (int)force;
     double cand_per_query = 0.0;
-    const int64_t ns = std::min<int64_t>(nq, 1024);
+    // the sample is walked by the warp kernel (count form): a warp finishes a 2000-row query in ~100 rounds of
+    // independent loads where a single thread needs 2000 dependent ones (3.9 ms for the sample alone, profiles/)
+    const int64_t ns = std::min<int64_t>(nq, 256);
     if (force == 2 || force == 1)
     {
-      const u32 stride = (u32)(nq / ns);
-      VI_CUDA_TRY(cudaMemsetAsync(d_vis, 0, 8, st));
-      k_search<false><<<(u32)((ns + 127) / 128), 128, 0, st>>>(ctx->t_node, ctx->t_src, d_queries, ctx->dims, (u32)ns, stride,
-                                                               proximity, d_offsets, nullptr, nullptr, 0, d_vis);
+      int rc = sw_launch(ctx, SW_MODE_COUNT, d_queries, ns, (u32)(nq / ns), proximity, d_offsets, nullptr, nullptr, 0, 0);
+      if (rc != VI_OK) return rc;
       k_scan_i64<<<1, 1024, 0, st>>>(d_offsets, (u32)ns);
       i64 stot = 0;
-      VI_CUDA_TRY(cudaMemcpyAsync(&vis, d_vis, 8, cudaMemcpyDeviceToHost, st));
+      SwCtl h{};
+      VI_CUDA_TRY(cudaMemcpyAsync(&h, d_ctl, sizeof(SwCtl), cudaMemcpyDeviceToHost, st));
       VI_CUDA_TRY(cudaMemcpyAsync(&stot, d_offsets + ns, sizeof(i64), cudaMemcpyDeviceToHost, st));
       VI_CUDA_TRY(cudaStreamSynchronize(st));
+      if ((rc = sw_check(ctx, h)) != VI_OK) return rc;
       cand_per_query = (double)stot / (double)ns;
-      if (force == 2) path = ((double)vis / (double)ns >= (double)sw_env("VI_B200_SEARCH_WARP_VISITS", 96, 1, 1u << 30)) ? 1 : 0;
-      vis = 0;
+      if (force == 2)
+        path = ((double)h.visits / (double)ns >= (double)sw_env("VI_B200_SEARCH_WARP_VISITS", 96, 1, 1u << 30)) ? 1 : 0;
     }
     ctx->search_path = path;
     if (path == 0)
@@ -497,7 +508,7 @@ int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proxim
       {
         // pool size from the sample: candidates per query + half a chunk of slack per query, 30 % head room
         const double est = (cand_per_query * 1.3 * SW_CHUNK / SW_CHUNK_IDS + SW_CHUNK) * (double)nq + 65536.0;
-        int64_t need = (int64_t)std::min(est, 4.0e9);  // at most 32 GB; what does not fit is walked twice
+        int64_t need = (int64_t)std::min(est, 4.0e9);  // at most 32 GB (32-bit slot indexes); what does not fit is walked twice
         const u32 cap_env = sw_env("VI_B200_SEARCH_POOL_SLOTS", 0, 0, 0x7fffffffu);
         if (cap_env) need = cap_env;
         if (sw_ensure(&ctx->sw_pool, &ctx->sw_pool_cap, need) != cudaSuccess ||
@@ -507,7 +518,7 @@ int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proxim
           pool = false;
         }
       }
-      int rc = sw_launch(ctx, pool ? SW_MODE_POOL : SW_MODE_COUNT, d_queries, nq, proximity, d_offsets, nullptr, nullptr, 0, 0);
+      int rc = sw_launch(ctx, pool ? SW_MODE_POOL : SW_MODE_COUNT, d_queries, nq, 1u, proximity, d_offsets, nullptr, nullptr, 0, 0);
       if (rc != VI_OK) return rc;
       k_scan_i64<<<1, 1024, 0, st>>>(d_offsets, (u32)nq);
       SwCtl h{};
@@ -547,7 +558,7 @@ int vi_search_impl(vi_ctx* ctx, const float* d_queries, int64_t nq, float proxim
             ctx->sw_pool, ctx->sw_head, d_offsets, (u32)nq, d_ids, cap);
       if (!from_pool || ctx->sw_pool_overflow)
       {
-        int rc = sw_launch(ctx, SW_MODE_FILL, d_queries, nq, proximity, d_offsets, d_ids, ctx->search_src, cap, from_pool ? 1 : 0);
+        int rc = sw_launch(ctx, SW_MODE_FILL, d_queries, nq, 1u, proximity, d_offsets, d_ids, ctx->search_src, cap, from_pool ? 1 : 0);
         if (rc != VI_OK) return rc;
         SwCtl h{};
         VI_CUDA_TRY(cudaMemcpyAsync(&h, d_ctl, sizeof(SwCtl), cudaMemcpyDeviceToHost, st));

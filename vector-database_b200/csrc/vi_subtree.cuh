@@ -195,6 +195,7 @@ struct SubEnv
   u32 overflow_base;
   u32 t_cap;
   u32 root_depth;     // depth of the sub-tree's root: a node's order list is ord[(depth - root_depth) & 1]
+  int sql;            // VI_MODE_SQL: min variance at depth 1 only, null Dimension / Mid when Stdev = 0
   u32* counters;      // global: [0] overflow rows used, [1] error, [2] float32 fallbacks, [3] work cursor
   u32* lvlp;          // shared: points / ranges per depth (accounting)
   u32* lvlr;
@@ -343,7 +344,7 @@ __device__ __forceinline__ u32 sub_team_split(const SubCtx& c, const SubEnv& env
   }
   int dim = bidx;
   float mid = qfx_mid((i64)bs1, m, c.qinv);
-  bool welford = false;
+  bool welford = false, null_dim = false;
   if (bkey < (((u64)m * (u64)m) << (2 * VI_QFX_MIN_RES_BITS)))  // poorly resolved (team-uniform): float32 statistics
   {
     if (tl == 0) atomicAdd(&env.counters[2], 1u);
@@ -351,6 +352,7 @@ __device__ __forceinline__ u32 sub_team_split(const SubCtx& c, const SubEnv& env
     dim = eb.idx;
     mid = eb.mean;
     welford = true;
+    null_dim = env.sql != 0 && eb.key == 0.f;  // Stdev = 0 (DDL.sql:193-194)
   }
   // pivot id and stable partition; lane tl looks after points tl, tl+8, ... (one round for m <= 8, else four)
   u32 nlo;
@@ -420,8 +422,8 @@ __device__ __forceinline__ u32 sub_team_split(const SubCtx& c, const SubEnv& env
   }
   if (tl == 0)
   {
-    env.t.t_dim[nd.row] = dim;
-    env.t.t_mid[nd.row] = mid;
+    env.t.t_dim[nd.row] = null_dim ? VI_DIM_NULL : dim;
+    env.t.t_mid[nd.row] = null_dim ? __int_as_float(0x7fc00000) : mid;
     env.t.t_id[nd.row] = pivot;
   }
   return nlo;
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(SUB_WARPS * 32, 2)
 k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ g_sub_perm, const i64* __restrict__ g_sub_pid,
                const float* __restrict__ rows, int ld, int dims, float qk, double qinv, TableOut t, int* __restrict__ t_src,
                u32 row_base, u32 overflow_base, u32 t_cap, u32* __restrict__ counters,
-               unsigned long long* __restrict__ lvl_points, unsigned long long* __restrict__ lvl_ranges, int T)
+               unsigned long long* __restrict__ lvl_points, unsigned long long* __restrict__ lvl_ranges, int T, int sql)
 {
   __shared__ u32 s_lvlp[64], s_lvlr[64];
   __shared__ u32 s_ncnt[SUB_WARPS];
@@ -478,6 +480,7 @@ k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ g_sub_perm, const i
   env.overflow_base = overflow_base;
   env.t_cap = t_cap;
   env.counters = counters;
+  env.sql = sql;
   env.lvlp = s_lvlp;
   env.lvlr = s_lvlr;
 
@@ -550,7 +553,7 @@ k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ g_sub_perm, const i
         if (lane == 0) counters[1] = 2u;  // splitting a depth-62 range: rangeId overflow (IndexBuilder.cs:99)
         break;
       }
-      const bool mx = (depth & 1u) == 0u;
+      const bool mx = sql ? depth != 1u : (depth & 1u) == 0u;  // DDL.sql:151,155 / IndexBuilder.cs:128-129
       const int ob = (int)((depth - env.root_depth) & 1u);
       const SubNode* nodes = reinterpret_cast<const SubNode*>(sub_base() + c.o_nodes[cur]);
       SubNode* nnodes = reinterpret_cast<SubNode*>(sub_base() + c.o_nodes[cur ^ 1]);

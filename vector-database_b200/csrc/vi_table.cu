@@ -42,7 +42,7 @@ __global__ void k_gather_rows(const u32* __restrict__ order, const i64* __restri
   t_mid[i] = mid[o];
   t_id[i] = id[o];
   t_src[i] = -1;  // no vectors behind an imported table: no candidate verification
-  if (r < 0 || d < -1 || d >= dims) atomicOr(bad, 1u);            // not a RangeID / Dimension of this index
+  if (r < 0 || (d < -1 && d != VI_DIM_NULL) || d >= dims) atomicOr(bad, 1u);  // not a RangeID / Dimension of this index
   if (i > 0 && rid_sorted[i - 1] == r) atomicOr(bad, 2u);          // duplicate RangeID
   if (i == 0 && r != 0) atomicOr(bad, 4u);                         // no root row
 }
@@ -65,7 +65,7 @@ __global__ void k_link_children(const i64* __restrict__ t_rid, const int* __rest
   if (i >= n) return;
   const i64 r = t_rid[i];
   int lo = -1, hi = -1;
-  if (t_dim[i] >= 0 && r <= (0x7fffffffffffffffLL - 2) / 2)  // children 2r+1, 2r+2 (IndexBuilder.cs:99,104)
+  if ((t_dim[i] >= 0 || t_dim[i] == VI_DIM_NULL) && r <= (0x7fffffffffffffffLL - 2) / 2)  // children 2r+1, 2r+2 (IndexBuilder.cs:99,104)
   {
     lo = find_row(t_rid, n, 2 * r + 1);
     hi = find_row(t_rid, n, 2 * r + 2);
@@ -81,9 +81,9 @@ __global__ void k_pack_nodes_t(const int* __restrict__ t_dim, const float* __res
   if (i >= n) return;
   const int d = t_dim[i];
   int4 v;
-  v.x = d;
+  v.x = d == VI_DIM_NULL ? VI_NODE_BOTH : d;
   v.y = __float_as_int(t_mid[i]);
-  if (d < 0)
+  if (d < 0 && d != VI_DIM_NULL)
   {
     const u64 id = (u64)t_id[i];  // leaf: the TextID rides in the child slots (same packing as vi_build.cu)
     v.z = (int)(u32)id;
@@ -167,7 +167,7 @@ int vi_ranges_load_impl(vi_ctx* ctx, const int64_t* rid, const int32_t* dim, con
   TRY_OR_CLEAN(cudaGetLastError());
 #undef TRY_OR_CLEAN
   cleanup();
-  if (bad & 1u) return ctx->fail(VI_ERR_INVALID_ARG, "range table: negative RangeID or Dimension outside [-1, dims)");
+  if (bad & 1u) return ctx->fail(VI_ERR_INVALID_ARG, "range table: negative RangeID or Dimension outside [-1, dims) (VI_DIM_NULL = -3 is a null Dimension)");
   if (bad & 2u) return ctx->fail(VI_ERR_INVALID_ARG, "range table: duplicate RangeID");
   if (bad & 4u) return ctx->fail(VI_ERR_INVALID_ARG, "range table: no row for RangeID 0");
   ctx->t_rows = n;
@@ -179,18 +179,22 @@ int vi_ranges_load_impl(vi_ctx* ctx, const int64_t* rid, const int32_t* dim, con
 
 // ---- record ingest -------------------------------------------------------------------------------------------------
 // one thread per (record, 4-byte word): word 0..1 = id, 2.. = vector
+// idw = 2: FileRangeStore records; idw = 0: bare rows (an HDF5 data set), ids are first_id, first_id + 1, ...
 __global__ void k_split_records(const u32* __restrict__ rec, u32 words, u32 n, int dims, int ld, i64* __restrict__ ids,
-                                float* __restrict__ rows)
+                                float* __restrict__ rows, u32 idw = 2, i64 first_id = 0)
 {
   const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const u64 r = t / words;
   const u32 w = (u32)(t % words);
   if (r >= n) return;
   const u32 x = rec[t];
-  if (w < 2) reinterpret_cast<u32*>(ids + r)[w] = x;
-  else rows[r * ld + (w - 2)] = __uint_as_float(x);
-  if (w == 2)
+  if (w < idw) reinterpret_cast<u32*>(ids + r)[w] = x;
+  else rows[r * ld + (w - idw)] = __uint_as_float(x);
+  if (w == idw)
+  {
+    if (idw == 0) ids[r] = first_id + (i64)r;
     for (int c = dims; c < ld; ++c) rows[r * ld + c] = 0.f;  // padding columns
+  }
 }
 
 int vi_reserve_for_add(vi_ctx* ctx, int64_t n);  // vi_abi.cu: grows the point store for n more points
@@ -257,9 +261,25 @@ static bool parallel_pread(int fd, char* dst, size_t bytes, off_t offset, unsign
   return ok;
 }
 
+static int add_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, double* read_ms, double* total_ms,
+                         u32 idw, i64 first_id);
+
 int vi_points_add_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, double* read_ms, double* total_ms)
 {
-  const size_t rec_bytes = 8 + 4 * (size_t)ctx->dims;
+  return add_file_impl(ctx, path, offset_bytes, n, read_ms, total_ms, 2u, 0);
+}
+
+// bare float32 rows (the contiguous storage of an HDF5 data set, vi_hdf5.cu): ids first_id, first_id + 1, ...
+int vi_points_add_rows_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, int64_t first_id,
+                                 double* read_ms, double* total_ms)
+{
+  return add_file_impl(ctx, path, offset_bytes, n, read_ms, total_ms, 0u, first_id);
+}
+
+static int add_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes, int64_t n, double* read_ms, double* total_ms,
+                         u32 idw, i64 first_id)
+{
+  const size_t rec_bytes = 4 * (size_t)idw + 4 * (size_t)ctx->dims;
   FILE* f = fopen(path, "rb");
   if (!f) return ctx->fail(VI_ERR_INVALID_ARG, std::string("cannot open ") + path + ": " + strerror(errno));
   if (n < 0)  // to the end of the file
@@ -328,11 +348,12 @@ int vi_points_add_file_impl(vi_ctx* ctx, const char* path, int64_t offset_bytes,
     e = cudaMemcpyAsync(d[b], h[b], (size_t)k * rec_bytes, cudaMemcpyHostToDevice, cs[b]);
     if (e != cudaSuccess) break;
     // (ctx->n is only advanced below: the kernel of this batch writes behind the points of the batches before it)
-    const u32 words = 2u + (u32)ctx->dims;
+    const u32 words = idw + (u32)ctx->dims;
     const u64 total = (u64)k * words;
     k_split_records<<<(u32)((total + 255) / 256), 256, 0, cs[b]>>>(d[b], words, (u32)k, ctx->dims, ctx->ld,
                                                                   ctx->ids + n0 + done,
-                                                                  ctx->rows + (size_t)(n0 + done) * ctx->ld);
+                                                                  ctx->rows + (size_t)(n0 + done) * ctx->ld, idw,
+                                                                  first_id + done);
     done += k;
     b ^= 1;
   }

@@ -28,6 +28,8 @@ VI_OK, VI_ERR_INVALID_ARG, VI_ERR_OVERFLOW, VI_ERR_NOT_IMPLEMENTED, VI_ERR_STATE
     VI_ERR_CUDA = range(8)
 MODE_EXACT = 0
 MODE_FAST = 1
+MODE_SQL = 2   # dbo.BuildIndex's rules (DDL.sql:44-202); Dimension DIM_NULL / Mid NaN = null
+DIM_NULL = -3
 
 _i64p = ctypes.POINTER(ctypes.c_int64)
 _i32p = ctypes.POINTER(ctypes.c_int32)
@@ -53,13 +55,42 @@ ALLTOALLV_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 
 # every symbol include/vi_b200.h declares
 EXPORTS = ["vi_abi_version", "vi_create", "vi_destroy", "vi_last_error", "vi_points_reserve", "vi_points_add",
-           "vi_points_add_device", "vi_points_add_records", "vi_points_add_file", "vi_points_count", "vi_build",
+           "vi_points_add_device", "vi_points_add_records", "vi_points_add_file", "vi_hdf5_dataset_info", "vi_hdf5_last_error", "vi_hdf5_read_rows",
+           "vi_points_add_hdf5", "vi_points_count", "vi_build",
            "vi_build_levels", "vi_range_count", "vi_ranges_copy", "vi_ranges_load", "vi_textindex_copy", "vi_search", "vi_search_begin",
            "vi_search_fetch", "vi_search_topk", "vi_search_device", "vi_search_verify",
            "vi_comm_unique_id", "vi_comm_init", "vi_comm_stats", "vi_set_collective", "vi_shared_rows", "vi_table_replicate",
            "vi_table_device", "vi_stream", "vi_debug_divcheck"]
 
 _lib = None
+
+
+def hdf5_dataset_info(path: str, dataset: str):
+    """(rows, cols, numpy dtype, byte offset of the data) of a contiguous HDF5 data set -- Program.cs:183-222
+    GetHdf5DatasetSize.  Host only (no device is touched).  ValueError("Invalid rank.") as the reference."""
+    L = load_library()
+    rows, cols, off = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    cls, size = ctypes.c_int32(0), ctypes.c_int32(0)
+    # no context (no device needed): the error text is the calling thread's vi_hdf5_last_error()
+    rc = L.vi_hdf5_dataset_info(None, os.fsencode(path), dataset.encode(), ctypes.byref(rows), ctypes.byref(cols),
+                                ctypes.byref(cls), ctypes.byref(size), ctypes.byref(off))
+    if rc != 0:
+        raise ValueError((L.vi_hdf5_last_error() or b"").decode() or f"vi_hdf5_dataset_info rc={rc}")
+    kind = {0: "i", 1: "f"}[cls.value]
+    return rows.value, cols.value, np.dtype(f"<{kind}{size.value}"), off.value
+
+
+def hdf5_read(path: str, dataset: str, first_row: int = 0, n: Optional[int] = None) -> np.ndarray:
+    """Rows [first_row, first_row + n) of a contiguous HDF5 data set into a numpy array (the `/test` queries)."""
+    L = load_library()
+    rows, cols, dt, _ = hdf5_dataset_info(path, dataset)
+    if n is None:
+        n = rows - first_row
+    out = np.empty((n, cols), dt)
+    rc = L.vi_hdf5_read_rows(None, os.fsencode(path), dataset.encode(), first_row, n, out.ctypes.data, out.nbytes)
+    if rc != 0:
+        raise ValueError((L.vi_hdf5_last_error() or b"").decode() or f"vi_hdf5_read_rows rc={rc}")
+    return out
 
 
 def load_library() -> ctypes.CDLL:
@@ -93,6 +124,12 @@ def load_library() -> ctypes.CDLL:
     L.vi_points_add_records.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32]
     L.vi_points_add_file.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    L.vi_hdf5_dataset_info.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, _i64p, _i64p, _i32p, _i32p, _i64p]
+    L.vi_hdf5_last_error.argtypes = []
+    L.vi_hdf5_last_error.restype = ctypes.c_char_p
+    L.vi_hdf5_read_rows.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, vp, ctypes.c_int64]
+    L.vi_points_add_hdf5.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.vi_search.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, _i64p, _i64p, ctypes.c_int64,
                             _i64p]
     L.vi_search_begin.argtypes = [vp, _f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, _i64p]
@@ -114,8 +151,8 @@ def load_library() -> ctypes.CDLL:
     L.vi_debug_divcheck.argtypes = [vp, ctypes.c_uint64, ctypes.c_int64, _i64p]
     L.vi_stream.restype = vp
     for name in EXPORTS:
-        if name not in ("vi_destroy", "vi_last_error", "vi_points_count", "vi_range_count", "vi_stream",
-                        "vi_abi_version"):
+        if name not in ("vi_destroy", "vi_last_error", "vi_hdf5_last_error", "vi_points_count", "vi_range_count",
+                        "vi_stream", "vi_abi_version"):
             getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L
@@ -222,6 +259,15 @@ class Context:
         """Streams records from a file (two pinned buffers). Returns (read_ms, total_ms)."""
         rd, tot = ctypes.c_double(0), ctypes.c_double(0)
         self._check(self._L.vi_points_add_file(self._h, os.fsencode(path), offset_bytes, n, dims, ctypes.byref(rd),
+                                               ctypes.byref(tot)))
+        return rd.value, tot.value
+
+    def add_hdf5(self, path: str, dataset: str = "/train", first_row: int = 0, n: int = -1, first_id: Optional[int] = None):
+        """Streams float32 rows of an HDF5 data set (Program.cs:224-260 GetHdf5Dataset); ids = row indexes unless
+        first_id is given. Returns (read_ms, total_ms)."""
+        rd, tot = ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self._L.vi_points_add_hdf5(self._h, os.fsencode(path), dataset.encode(), first_row, n,
+                                               first_row if first_id is None else first_id, ctypes.byref(rd),
                                                ctypes.byref(tot)))
         return rd.value, tot.value
 
