@@ -542,6 +542,7 @@ def main():
     info = infos[-1]
     levels = ctx.levels()
     whole_b, stats_b = algorithmic_bytes(levels, DIMS)
+    survey_b = sum(l.points * (4 * DIMS + 28) + l.ranges * 40 for l in levels)
     stats_ms = sum(l.stats_ms for l in levels) + info.subtree_ms  # level passes + the sub-tree kernel
     part_ms = sum(l.partition_ms for l in levels)
     peak, peak_src = peaks()
@@ -557,6 +558,10 @@ def main():
                                 "(profiles/r1_ncu_final.md)",
                 "algorithmic_bytes_per_launch": stats_b / max(n_stats_launch, 1),
                 "avg_launch_ms": stats_ms / max(n_stats_launch, 1),
+                # SURVEY.md 8(d) as written (the level-by-level algorithm, every row read at every level): 412 B per point
+                # visit + 40 B per range at D = 96 -- what the surveyed algorithm moves, divided by what this build takes
+                "survey_8d": {"algorithmic_bytes": survey_b, "achieved": survey_b / (ms_per_step / 1e3) / 1e9,
+                              "frac": survey_b / (ms_per_step / 1e3) / 1e9 / peak},
                 "whole_build": {"algorithmic_bytes": whole_b, "achieved": whole_b / (ms_per_step / 1e3) / 1e9,
                                 "frac": whole_b / (ms_per_step / 1e3) / 1e9 / peak, "stats_ms": stats_ms,
                                 "partition_ms": part_ms},
@@ -606,6 +611,17 @@ def main():
         del exact_table
         ctx.build(vi.MODE_FAST)
     del fast_table
+    # ---- dbo.BuildIndex's rules (VI_MODE_SQL): same kernels, different alternation / null rows ----
+    sms_, sinfos, _ = timed_builds(vi.MODE_SQL, 2, 3)
+    st = ctx.ranges()
+    result["sql_mode"] = {"value": n / (sum(sms_) / len(sms_) / 1e3), "unit": "vectors/s", "ms_per_step": sum(sms_) / len(sms_),
+                          "steps": 3, "warmup": 2, "ranges": int(sinfos[-1].ranges), "levels": int(sinfos[-1].levels),
+                          "null_dimension_rows": int((st[1] == vi.DIM_NULL).sum()), "table_checksum": table_checksum(*st),
+                          "note": "dbo.BuildIndex (DDL.sql:44-202): max / MIN / max / max ... by depth, root ties high, "
+                                  "Dimension = Mid = null where Stdev = 0; bit-identical to oracle mode 2 (tests/test_sql_mode.py)"}
+    log(f"sql-mode build: {result['sql_mode']['ms_per_step']:.2f} ms/step, {result['sql_mode']['ranges']} ranges")
+    del st
+    ctx.build(vi.MODE_FAST)
 
     # ---- search ---------------------------------------------------------------------------------------------------
     if not args.no_search:
@@ -628,9 +644,14 @@ def main():
             b.record(stream)
             torch.cuda.synchronize()
             sms = a.elapsed_time(b) / reps
-            bytes_q = nq * 4 * DIMS + 2 * visits * 16 + total * 8  # count pass + fill pass both walk the table
+            # point-lookup batches are walked twice, one thread per query (count, fill); batches that visit >= 96 rows
+            # per query once, a warp per query, the candidates parked in a device pool (write + read) and gathered
+            warp = visits / nq >= 96
+            bytes_q = nq * 4 * DIMS + (1 if warp else 2) * visits * 16 + (3 if warp else 1) * total * 8
             search[f"p={p}"] = {"queries_per_sec": nq / (sms / 1e3), "ms": sms, "queries": nq, "candidates": int(total),
-                                "visits": int(visits), "algorithmic_gbs": bytes_q / (sms / 1e3) / 1e9}
+                                "visits": int(visits), "algorithmic_gbs": bytes_q / (sms / 1e3) / 1e9,
+                                "kernel": "k_search_warp<pool> + k_search_gather (one walk)" if warp
+                                else "k_search<count> + k_search<fill> (two walks)"}
             log(f"search p={p}: {sms:.2f} ms for {nq} queries, {total} candidates, {visits} visits")
             del ids_out
         result["search"] = search
