@@ -23,8 +23,11 @@ def main():
     ctx.reserve(n, d)
     ctx.add_device(ids_d.data_ptr(), rows_d.data_ptr(), n, d)
     del rows_d
-    for tb in os.environ.get("SWEEP_T_BIG", "512,256,128,64").split(","):
+    import itertools
+    for tb, wch in itertools.product(os.environ.get("SWEEP_T_BIG", "512,256,128,64").split(","),
+                                     os.environ.get("SWEEP_WIDE_CH", "6").split(",")):
         os.environ["VI_B200_T_BIG"] = tb
+        os.environ["VI_B200_WIDE_CH"] = wch
         ctx.build(vi.MODE_FAST)
         best = None
         for _ in range(3):
@@ -34,7 +37,7 @@ def main():
                 best = (info.build_ms, lv, info)
         ms, lv, info = best
         cs = bench.table_checksum(*ctx.ranges())
-        print(f"T_BIG={tb} build {ms:.2f} ms stats {sum(l.stats_ms for l in lv):.2f} partition "
+        print(f"T_BIG={tb} WIDE_CH={wch} build {ms:.2f} ms stats {sum(l.stats_ms for l in lv):.2f} partition "
               f"{sum(l.partition_ms for l in lv):.2f} subtree {info.subtree_ms:.2f} launches {info.kernel_launches} "
               f"checksum {cs}", flush=True)
         print("   stats_ms/level:", " ".join(f"{l.stats_ms:.2f}" for l in lv[:20]), flush=True)

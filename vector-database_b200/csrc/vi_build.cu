@@ -428,6 +428,15 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   const u32 wr = env_u32("VI_B200_WARP_ROWS", 1, 0, 3);
   env.shp = fast_shape(ctx->ld, (wr & 2) != 0);
   env.shp_big = fast_shape(ctx->ld, (wr & 1) != 0);
+  // rows wider than 128 floats: the warp-per-range kernel with 6 float4 per lane holds 48 64-bit accumulators (255
+  // registers, 8 warps per SM: latency-bound); fewer columns per pass and several passes over the range's rows keep
+  // more warps resident (the passes read disjoint columns: no byte is read twice)
+  if (ctx->ld / 4 > 128)
+  {
+    const u32 wch = env_u32("VI_B200_WIDE_CH", 6, 1, 6);
+    const int ch = wch >= 6 ? 6 : wch >= 4 ? 4 : wch >= 3 ? 3 : wch >= 2 ? 2 : 1;
+    env.shp = {32, ch, (ctx->ld / 4) == 32 * ch};
+  }
   env.chx = exact_chx(ctx->dims);
   env.qk = 1.0f;
   env.qinv = 1.0;
