@@ -15,6 +15,22 @@ for p in (ROOT, os.path.join(ROOT, "vector-database_b200")):
 pytestmark = pytest.mark.gpu
 
 
+def _data(n, d, seed, kind):
+    from vectorindex import synthetic as ds
+    ids, rows = getattr(ds, "unit_gaussian" if kind == "sql_dups" else "uniform" if kind == "clustered" else kind)(n, d, seed=seed)
+    ids = ids * 3 + 7
+    if kind == "clustered":
+        # a tight cluster (|x| ~ 1e-7) plus outliers that set the quantisation scale: below the root the ranges are
+        # poorly resolved for the integer statistics -> the build starts over with fewer shared levels
+        rows = (rows * np.float32(1e-7)).astype(np.float32)
+        rows[::7, 3] += np.float32(1.5)
+    if kind == "sql_dups":
+        # VI_MODE_SQL over copies of a few vectors: Stdev = 0 ranges (null Dimension rows) inside the owned sub-trees
+        rows = rows.copy()
+        rows[: n // 3] = rows[np.random.default_rng(seed).integers(n // 3, n // 3 + 300, n // 3)]
+    return ids, rows
+
+
 def _worker(rank, world, port, q, n, d, seed, kind, transport="nccl"):
     import torch.distributed as dist
     import vectorindex as vi
@@ -24,13 +40,8 @@ def _worker(rank, world, port, q, n, d, seed, kind, transport="nccl"):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    ids, rows = getattr(ds, "uniform" if kind == "clustered" else kind)(n, d, seed=seed)
-    ids = ids * 3 + 7
-    if kind == "clustered":
-        # a tight cluster (|x| ~ 1e-7) plus outliers that set the quantisation scale: below the root the ranges are
-        # poorly resolved for the integer statistics -> the build starts over with fewer shared levels
-        rows = (rows * np.float32(1e-7)).astype(np.float32)
-        rows[::7, 3] += np.float32(1.5)
+    ids, rows = _data(n, d, seed, kind)
+    mode = vi.MODE_SQL if kind == "sql_dups" else vi.MODE_FAST
     lo, hi = rank * n // world, (rank + 1) * n // world
     if kind == "uniform" and rank == world - 1:
         lo = hi = n  # an empty shard on the last rank ...
@@ -46,7 +57,7 @@ def _worker(rank, world, port, q, n, d, seed, kind, transport="nccl"):
     else:
         init_nccl(ctx, torch.device("cuda", rank))      # library-owned NCCL communicator
     # a search before the table is replicated must be refused (this rank holds only its own sub-trees)
-    info = ctx.build(vi.MODE_FAST)
+    info = ctx.build(mode)
     try:
         ctx.search(rows[:2], 0.0)
         refused = False
@@ -72,7 +83,8 @@ def _worker(rank, world, port, q, n, d, seed, kind, transport="nccl"):
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("n,d,seed,kind,transport", [(200_000, 96, 3, "unit_gaussian", "nccl"), (5000, 16, 5, "uniform", "nccl"),
                                                      (30_000, 24, 7, "unit_gaussian", "callbacks"),
-                                                     (20_000, 8, 9, "clustered", "nccl")])
+                                                     (20_000, 8, 9, "clustered", "nccl"),
+                                                     (60_000, 12, 11, "sql_dups", "nccl")])
 def test_sharded_build_equals_oracle(world, n, d, seed, kind, transport):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -110,12 +122,10 @@ def test_sharded_build_equals_oracle(world, n, d, seed, kind, transport):
                 assert int(rid[k]) not in union
                 union[int(rid[k])] = val
         owned_rows.append(len(rid) - shared)
-    ids, rows = getattr(ds, "uniform" if kind == "clustered" else kind)(n, d, seed=seed)
-    ids = ids * 3 + 7
-    if kind == "clustered":
-        rows = (rows * np.float32(1e-7)).astype(np.float32)
-        rows[::7, 3] += np.float32(1.5)
-    ref = oracle.build(ids, rows, oracle.MODE_QFX)
+    ids, rows = _data(n, d, seed, kind)
+    ref = oracle.build(ids, rows, oracle.MODE_SQL if kind == "sql_dups" else oracle.MODE_QFX)
+    if kind == "sql_dups":
+        assert (ref.dimension == -3).any()
     want = {int(r): (int(dm), int(np.float32(m).view(np.uint32)), int(i))
             for r, dm, m, i in zip(ref.range_id, ref.dimension, ref.mid, ref.id)}
     assert union == want

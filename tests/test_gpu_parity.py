@@ -589,3 +589,31 @@ def test_search_paths_agree_with_the_oracle(env, monkeypatch):
             cand = rout[roffs[i]:roffs[i + 1]]
             want = [int(k) for k in cand if oracle.distance_l2(rows[k], queries[i]) <= np.float32(dist)]
             assert vout[voffs[i]:voffs[i + 1]].tolist() == want
+
+
+@pytest.mark.parametrize("mode", [vi.MODE_EXACT, vi.MODE_FAST, vi.MODE_SQL])
+@pytest.mark.parametrize("n", [5, 3000, 400_000])
+def test_build_copy_equals_build_then_ranges_copy(mode, n):
+    # vi_build_copy: at 400k points the sub-tree list is taken in four slices whose row blocks are copied out while the
+    # next slice runs; the delivered table must be the one vi_ranges_copy returns, row for row
+    import torch
+    ids, rows = ds.unit_gaussian(n, 24, seed=n)
+    ids = ids * 2 + 1
+    cap = 2 * n + n // 8 + 1024
+    pin = [torch.empty(cap, dtype=t, pin_memory=True).numpy() for t in (torch.int64, torch.int32, torch.float32, torch.int64)]
+    for a in pin:
+        a[:] = 0
+    with vi.Context(0) as ctx:
+        ctx.reserve(n, 24)
+        ctx.add(ids, rows)
+        info, k = ctx.build_into(mode, *pin)
+        want = ctx.ranges()
+        assert k == info.ranges == len(want[0])
+        for got, w in zip(pin, want):
+            assert np.array_equal(got[:k].view(np.uint8), w.view(np.uint8))
+        # too small a destination: the build is complete, the copy is refused
+        small = [np.zeros(10, a.dtype) for a in pin]
+        if k > 10:
+            with pytest.raises(vi.VectorIndexError):
+                ctx.build_into(mode, *small)
+            assert np.array_equal(ctx.ranges()[0], want[0])

@@ -48,6 +48,7 @@ internal static partial class NativeMethods
   [LibraryImport(Lib)] public static partial long vi_points_count(IntPtr ctx);
   // ---- build, range table
   [LibraryImport(Lib)] public static partial int vi_build(IntPtr ctx, int mode, out BuildInfo info);
+  [LibraryImport(Lib)] public static unsafe partial int vi_build_copy(IntPtr ctx, int mode, out BuildInfo info, long* rangeId, int* dimension, float* mid, long* id, long cap, out long rows);
   [LibraryImport(Lib)] public static unsafe partial int vi_build_levels(IntPtr ctx, LevelInfo* levels, int cap, out int n);
   [LibraryImport(Lib)] public static partial long vi_range_count(IntPtr ctx);
   [LibraryImport(Lib)] public static unsafe partial int vi_ranges_copy(IntPtr ctx, long* rangeId, int* dimension, float* mid, long* id, long cap);

@@ -81,6 +81,7 @@ void vi_destroy(vi_ctx* ctx)
   cudaFree(ctx->sh_dev);
   if (ctx->sh_host) cudaFreeHost(ctx->sh_host);
   cudaFree(ctx->counters);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -234,6 +235,69 @@ int vi_build(vi_ctx* ctx, int32_t mode, vi_build_info* info)
   ctx->pending_nq = -1;
   int rc = vi_build_impl(ctx, mode);
   if (info) *info = ctx->info;
+  return rc;
+}
+
+// vi_build + vi_ranges_copy in one call: the dense row blocks the build's last kernel finishes first travel to the host
+// while it is still running (vi_build.cu run_subtrees / copy_out_rows); the rest follows when the build is done.
+int vi_build_copy(vi_ctx* ctx, int32_t mode, vi_build_info* info, int64_t* range_id, int32_t* dimension, float* mid,
+                  int64_t* id, int64_t cap, int64_t* rows)
+{
+  if (!ctx || !rows) return VI_ERR_INVALID_ARG;
+  *rows = 0;
+  if (mode != VI_MODE_EXACT && mode != VI_MODE_FAST && mode != VI_MODE_SQL)
+    return ctx->fail(VI_ERR_INVALID_ARG, "unknown build mode");
+  if (ctx->dims == 0) return ctx->fail(VI_ERR_STATE, "no points: vi_points_reserve / vi_points_add first");
+  if (ctx->world > 1 && mode == VI_MODE_EXACT)
+    return ctx->fail(VI_ERR_INVALID_ARG, "multi-rank build needs VI_MODE_FAST or VI_MODE_SQL (order-independent sums)");
+  VI_CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->pending_nq = -1;
+  ctx->out = vi_ctx::CopyOut();
+  ctx->out.rid = range_id;
+  ctx->out.dim = dimension;
+  ctx->out.mid = mid;
+  ctx->out.id = id;
+  ctx->out.cap = cap;
+  ctx->out.active = ctx->world == 1 && cap > 0;
+  int rc = vi_build_impl(ctx, mode);
+  const vi_ctx::CopyOut o = ctx->out;
+  ctx->out = vi_ctx::CopyOut();
+  if (info) *info = ctx->info;
+  cudaError_t e = cudaSuccess;
+  if (rc == VI_OK)
+  {
+    const int64_t k = ctx->t_rows;
+    *rows = k;
+    if (cap < k) rc = ctx->fail(VI_ERR_CAPACITY, "range buffers too small");
+    else if (k > 0)
+    {
+      // the build has synchronised its stream: what was not sent on the way goes now, [0, lo) and [hi, k)
+      cudaStream_t cs = ctx->copy_stream ? ctx->copy_stream : ctx->stream;
+      const int64_t lo = o.copied_hi > o.copied_lo ? o.copied_lo : k, hi = o.copied_hi > o.copied_lo ? o.copied_hi : k;
+      const int64_t part[2][2] = {{0, lo}, {hi, k}};
+      for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+      {
+        const int64_t a = part[i][0];
+        const size_t n = part[i][1] > a ? (size_t)(part[i][1] - a) : 0;
+        if (!n) continue;
+        if (range_id) e = cudaMemcpyAsync(range_id + a, ctx->t_rid + a, n * 8, cudaMemcpyDeviceToHost, cs);
+        if (dimension && e == cudaSuccess) e = cudaMemcpyAsync(dimension + a, ctx->t_dim + a, n * 4, cudaMemcpyDeviceToHost, cs);
+        if (mid && e == cudaSuccess) e = cudaMemcpyAsync(mid + a, ctx->t_mid + a, n * 4, cudaMemcpyDeviceToHost, cs);
+        if (id && e == cudaSuccess) e = cudaMemcpyAsync(id + a, ctx->t_id + a, n * 8, cudaMemcpyDeviceToHost, cs);
+      }
+    }
+  }
+  // copies may be in flight into the caller's buffers whatever the outcome
+  if (ctx->copy_stream)
+  {
+    const cudaError_t e2 = cudaStreamSynchronize(ctx->copy_stream);
+    if (e == cudaSuccess) e = e2;
+  }
+  {
+    const cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = e2;
+  }
+  if (e != cudaSuccess && rc == VI_OK) return ctx->fail_cuda(e, "vi_build_copy", __FILE__, __LINE__);
   return rc;
 }
 

@@ -401,7 +401,8 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   // range-size classes (see vi_stats_fast.cuh / vi_stats_exact.cuh); defaults from scripts/sweep.py on 10M x 96
   // (profiles/r1_sweep.txt); the variables exist for such sweeps
   env.t_team = env_u32("VI_B200_T_TEAM", 32, 2, VI_MAX_ROWS_PER_LANE);
-  const u32 t_big_fast = env_u32("VI_B200_T_BIG", 512, VI_MIN_BIG, VI_MAX_ROWS_PER_LANE);  // raised to t_sub + 1 below
+  // (rows wider than 512 floats: a 128-row range is already 400 KB, enough for a CTA; profiles/r2_sweep_768.txt)
+  const u32 t_big_fast = env_u32("VI_B200_T_BIG", ctx->ld > 512 ? 128 : 512, VI_MIN_BIG, VI_MAX_ROWS_PER_LANE);
   const u32 t_big_exact = env_u32("VI_B200_T_BIG_EXACT", 512, VI_MIN_BIG, 1u << 30);
   env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
   env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 8, 0, 8);  // 0 = cp.async ring
@@ -433,7 +434,7 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   // more warps resident (the passes read disjoint columns: no byte is read twice)
   if (ctx->ld / 4 > 128)
   {
-    const u32 wch = env_u32("VI_B200_WIDE_CH", 6, 1, 6);
+    const u32 wch = env_u32("VI_B200_WIDE_CH", 1, 1, 6);  // 1M x 768: 18.1 -> 15.6 ms per build (profiles/r2_sweep_768.txt)
     const int ch = wch >= 6 ? 6 : wch >= 4 ? 4 : wch >= 3 ? 3 : wch >= 2 ? 2 : 1;
     env.shp = {32, ch, (ctx->ld / 4) == 32 * ch};
   }
@@ -503,6 +504,28 @@ static void launch_big_fast(vi_ctx* ctx, BuildEnv& env, const LevelDev* lvp, con
   ++env.launches;
 }
 
+// vi_build_copy: rows [r0, r1) of the table are final once the work enqueued on the build stream so far has run; send
+// them to the caller's buffers on the copy stream.  Blocks are handed over in increasing row order.
+static int copy_out_rows(vi_ctx* ctx, BuildEnv& env, int64_t r0, int64_t r1)
+{
+  vi_ctx::CopyOut& o = ctx->out;
+  if (!o.active) return VI_OK;
+  r1 = std::min(r1, o.cap);  // what does not fit is reported by vi_build_copy at the end
+  if (r1 <= r0) return VI_OK;
+  if (!ctx->copy_stream) VI_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  cudaEvent_t ev = env_event(ctx, env);
+  VI_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+  const size_t n = (size_t)(r1 - r0);
+  cudaStream_t cs = ctx->copy_stream;
+  if (o.rid) VI_CUDA_TRY(cudaMemcpyAsync(o.rid + r0, ctx->t_rid + r0, n * 8, cudaMemcpyDeviceToHost, cs));
+  if (o.dim) VI_CUDA_TRY(cudaMemcpyAsync(o.dim + r0, ctx->t_dim + r0, n * 4, cudaMemcpyDeviceToHost, cs));
+  if (o.mid) VI_CUDA_TRY(cudaMemcpyAsync(o.mid + r0, ctx->t_mid + r0, n * 4, cudaMemcpyDeviceToHost, cs));
+  if (o.id) VI_CUDA_TRY(cudaMemcpyAsync(o.id + r0, ctx->t_id + r0, n * 8, cudaMemcpyDeviceToHost, cs));
+  if (o.copied_hi == o.copied_lo) o.copied_lo = r0;
+  o.copied_hi = r1;
+  return VI_OK;
+}
+
 // Finishes every range on the sub-tree list (vi_subtree.cuh); advances s.row_next past their rows.
 static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* rows)
 {
@@ -519,25 +542,49 @@ static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* 
   TableOut tout{ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high};
   SubList sl{ctx->sub_start, ctx->sub_count, ctx->sub_rid, ctx->sub_row, ctx->sub_depth};
   const size_t smem = (size_t)SUB_WARPS * sub_smem_bytes_per_warp(rows_max, ld);
-  const u32 grid = std::min<u32>((s.sub_cnt + SUB_WARPS - 1) / SUB_WARPS, (u32)VI_NUM_SMS * 2u);  // persistent warps, work cursor
+  // vi_build_copy: the list is taken in a few slices, and the dense row block of a finished slice (closed-form row
+  // numbers: sub-tree k starts at row_base + 2 * sub_start[k] - 2 * k) goes to the host while the next slice runs
+  const int nslice = (ctx->out.active && s.sub_cnt >= 8192u) ? 4 : 1;
+  u32 kb[5] = {0, 0, 0, 0, s.sub_cnt};
+  u32 sb[5] = {0, 0, 0, 0, s.sub_pos};
+  for (int i = 1; i < nslice; ++i)
+  {
+    kb[i] = (u32)((u64)s.sub_cnt * i / nslice);
+    VI_CUDA_TRY(cudaMemcpyAsync(&sb[i], ctx->sub_start + kb[i], 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (nslice > 1) VI_CUDA_TRY(cudaStreamSynchronize(st));
   cudaEvent_t e0 = env_event(ctx, env);
 #define CALL_SUB(CH, FULL)                                                                                                \
   do                                                                                                                      \
   {                                                                                                                       \
     VI_CUDA_TRY(cudaFuncSetAttribute(k_subtree_fast<CH, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-    k_subtree_fast<CH, FULL><<<grid, SUB_WARPS * 32, smem, st>>>(sl, s.sub_cnt, ctx->sub_perm, ctx->sub_pid, rows, ld, dims, \
+    k_subtree_fast<CH, FULL><<<grid, SUB_WARPS * 32, smem, st>>>(sl, k1, ctx->sub_perm, ctx->sub_pid, rows, ld, dims,       \
                                                                  env.qk, env.qinv, tout, ctx->t_src, row_base,            \
                                                                  overflow_base, (u32)ctx->t_cap, cnt, lvlp, lvlr,         \
-                                                                 rows_max, env.sql);                                      \
+                                                                 rows_max, env.sql, k0);                                  \
   } while (0)
   const int ch = std::min(4, (ld / 4 + 7) / 8);  // int4 columns per team lane and pass
   const bool sub_full = ld == 32 * ch && dims == ld;
-  if (ch <= 1) { if (sub_full) CALL_SUB(1, true); else CALL_SUB(1, false); }
-  else if (ch == 2) { if (sub_full) CALL_SUB(2, true); else CALL_SUB(2, false); }
-  else if (ch == 3) { if (sub_full) CALL_SUB(3, true); else CALL_SUB(3, false); }
-  else { if (sub_full) CALL_SUB(4, true); else CALL_SUB(4, false); }
+  for (int i = 0; i < nslice; ++i)
+  {
+    const u32 k0 = kb[i], k1 = nslice == 1 ? s.sub_cnt : kb[i + 1];
+    if (k1 <= k0) continue;
+    const u32 grid = std::min<u32>((k1 - k0 + SUB_WARPS - 1) / SUB_WARPS, (u32)VI_NUM_SMS * 2u);  // persistent warps, work cursor
+    if (i > 0) VI_CUDA_TRY(cudaMemsetAsync(cnt + 3, 0, 4, st));  // the work cursor
+    if (ch <= 1) { if (sub_full) CALL_SUB(1, true); else CALL_SUB(1, false); }
+    else if (ch == 2) { if (sub_full) CALL_SUB(2, true); else CALL_SUB(2, false); }
+    else if (ch == 3) { if (sub_full) CALL_SUB(3, true); else CALL_SUB(3, false); }
+    else { if (sub_full) CALL_SUB(4, true); else CALL_SUB(4, false); }
+    ++env.launches;
+    if (nslice > 1)
+    {
+      const int64_t r0 = (int64_t)row_base + 2 * (int64_t)sb[i] - 2 * (int64_t)k0;
+      const int64_t r1 = i + 1 == nslice ? (int64_t)overflow_base : (int64_t)row_base + 2 * (int64_t)sb[i + 1] - 2 * (int64_t)k1;
+      const int rc = copy_out_rows(ctx, env, r0, r1);
+      if (rc != VI_OK) return rc;
+    }
+  }
 #undef CALL_SUB
-  ++env.launches;
   cudaEvent_t e1 = env_event(ctx, env);
   unsigned long long h[130];
   VI_CUDA_TRY(cudaMemcpyAsync(h, ctx->sub_stats, sizeof(h), cudaMemcpyDeviceToHost, st));

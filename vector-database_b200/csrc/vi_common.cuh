@@ -145,6 +145,20 @@ struct vi_ctx
   const float* src_rows = nullptr;  // the row store the table's t_src indexes (rows, or own_rows after a multi-rank
                                     // build); null when the table has no vectors behind it (imported / replicated)
 
+  // vi_build_copy: host destinations of the range table; finished row blocks are copied out on copy_stream while the
+  // build's last kernel is still running (null = a plain vi_build)
+  struct CopyOut
+  {
+    i64* rid = nullptr;
+    int* dim = nullptr;
+    float* mid = nullptr;
+    i64* id = nullptr;
+    int64_t cap = 0;
+    int64_t copied_lo = 0, copied_hi = 0;  // rows [copied_lo, copied_hi) are already on their way
+    bool active = false;
+  } out;
+  cudaStream_t copy_stream = nullptr;
+
   vi_build_info info{};
   std::vector<vi_level_info> levels;
 

@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(SUB_WARPS * 32, 2)
 k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ g_sub_perm, const i64* __restrict__ g_sub_pid,
                const float* __restrict__ rows, int ld, int dims, float qk, double qinv, TableOut t, int* __restrict__ t_src,
                u32 row_base, u32 overflow_base, u32 t_cap, u32* __restrict__ counters,
-               unsigned long long* __restrict__ lvl_points, unsigned long long* __restrict__ lvl_ranges, int T, int sql)
+               unsigned long long* __restrict__ lvl_points, unsigned long long* __restrict__ lvl_ranges, int T, int sql,
+               u32 k0)
 {
   __shared__ u32 s_lvlp[64], s_lvlr[64];
   __shared__ u32 s_ncnt[SUB_WARPS];
@@ -487,7 +488,7 @@ k_subtree_fast(SubList sl, u32 nsub, const u32* __restrict__ g_sub_perm, const i
   for (;;)
   {
     u32 k = 0;
-    if (lane == 0) k = atomicAdd(&counters[3], 1u);
+    if (lane == 0) k = k0 + atomicAdd(&counters[3], 1u);  // this launch takes the sub-trees [k0, nsub)
     k = __shfl_sync(0xffffffffu, k, 0);
     if (k >= nsub) break;
     const u32 S = sl.start[k], n = sl.count[k];

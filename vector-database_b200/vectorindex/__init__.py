@@ -56,7 +56,7 @@ ALLTOALLV_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, 
 # every symbol include/vi_b200.h declares
 EXPORTS = ["vi_abi_version", "vi_create", "vi_destroy", "vi_last_error", "vi_points_reserve", "vi_points_add",
            "vi_points_add_device", "vi_points_add_records", "vi_points_add_file", "vi_hdf5_dataset_info", "vi_hdf5_last_error", "vi_hdf5_read_rows",
-           "vi_points_add_hdf5", "vi_points_count", "vi_build",
+           "vi_points_add_hdf5", "vi_points_count", "vi_build", "vi_build_copy",
            "vi_build_levels", "vi_range_count", "vi_ranges_copy", "vi_ranges_load", "vi_textindex_copy", "vi_search", "vi_search_begin",
            "vi_search_fetch", "vi_search_topk", "vi_search_device", "vi_search_verify",
            "vi_comm_unique_id", "vi_comm_init", "vi_comm_stats", "vi_set_collective", "vi_shared_rows", "vi_table_replicate",
@@ -115,6 +115,7 @@ def load_library() -> ctypes.CDLL:
     L.vi_points_count.argtypes = [vp]
     L.vi_points_count.restype = ctypes.c_int64
     L.vi_build.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(BuildInfo)]
+    L.vi_build_copy.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(BuildInfo), _i64p, _i32p, _f32p, _i64p, ctypes.c_int64, _i64p]
     L.vi_build_levels.argtypes = [vp, ctypes.POINTER(LevelInfo), ctypes.c_int32, _i32p]
     L.vi_range_count.argtypes = [vp]
     L.vi_range_count.restype = ctypes.c_int64
@@ -280,6 +281,15 @@ class Context:
         info = BuildInfo()
         self._check(self._L.vi_build(self._h, mode, ctypes.byref(info)))
         return info
+
+    def build_into(self, mode: int, rid: np.ndarray, dim: np.ndarray, mid: np.ndarray, oid: np.ndarray):
+        """vi_build_copy: build and deliver the range table into caller-owned (ideally pinned) arrays, the D2H copy
+        overlapped with the build's last kernel.  Returns (BuildInfo, rows)."""
+        info = BuildInfo()
+        k = ctypes.c_int64(0)
+        self._check(self._L.vi_build_copy(self._h, mode, ctypes.byref(info), _p(rid, _i64p), _p(dim, _i32p), _p(mid, _f32p),
+                                          _p(oid, _i64p), min(len(rid), len(dim), len(mid), len(oid)), ctypes.byref(k)))
+        return info, k.value
 
     def levels(self):
         n = ctypes.c_int32(0)
