@@ -109,6 +109,8 @@ def build(ids: np.ndarray, rows: np.ndarray, mode: int = MODE_LITERAL, root_rid:
                             -2 ** 31 if qe is None else qe)
     if rc == -2:
         raise OverflowError("rangeId overflow (IndexBuilder.cs:99,104 checked arithmetic)")
+    if rc == -4 and mode != MODE_LITERAL and np.isinf(rows).any():
+        raise ValueError("the qfx modes refuse +-Inf in the data (no fixed-point image)")
     if rc != 0:
         raise OracleError(f"vio_build rc={rc}")
     k = cnt.value

@@ -87,9 +87,9 @@ def build_qfx(ids, rows, sql=False):
     ids = [int(i) for i in ids]
     finite = np.abs(rows[np.isfinite(rows)])
     amax = np.float32(finite.max()) if finite.size else np.float32(0)
-    if np.isinf(np.abs(rows)).any():
-        e = 128
-    elif amax > 0:
+    if np.isinf(rows).any():
+        raise ValueError("the qfx modes refuse +-Inf (no fixed-point image); the literal mode takes it")
+    if amax > 0:
         _, e = np.frexp(amax)
         e = int(e)
     else:

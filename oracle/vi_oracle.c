@@ -113,8 +113,8 @@ int vio_qfx_exponent(const float* rows, int64_t n, int32_t d, int64_t ld)
       if (a > amax) amax = a; /* NaN never wins: comparisons with NaN are false */
     }
   int e = 0;
-  if (amax > 0.0f && !isinf(amax)) (void)frexpf(amax, &e);
-  else if (isinf(amax)) e = 128;
+  if (isinf(amax)) return INT32_MAX; /* +-Inf has no fixed-point image: the qfx modes refuse it (vio_build: VIO_ERR_ARG) */
+  if (amax > 0.0f) (void)frexpf(amax, &e);
   if (e < -96) e = -96;
   if (e > 128) e = 128;
   return e;
@@ -173,9 +173,10 @@ int vio_build_ex(int64_t n, int32_t d, int64_t ld, const int64_t* ids, const flo
   int qe = 0;
   float qk = 1.0f;
   double qinv = 1.0;
-  if (mode != 0)
+  if (mode != 0 && (n > 1 || qe_override != INT32_MIN))
   {
     qe = qe_override != INT32_MIN ? qe_override : vio_qfx_exponent(rows, n, d, ld);
+    if (qe == INT32_MAX) { rc = VIO_ERR_ARG; goto done; } /* +-Inf in the data: only the literal mode takes it */
     qk = ldexpf(1.0f, VIO_QBITS - qe);
     qinv = ldexp(1.0, qe - VIO_QBITS);
   }

@@ -617,3 +617,24 @@ def test_build_copy_equals_build_then_ranges_copy(mode, n):
             with pytest.raises(vi.VectorIndexError):
                 ctx.build_into(mode, *small)
             assert np.array_equal(ctx.ranges()[0], want[0])
+
+
+def test_fast_modes_refuse_infinity_exact_mode_takes_it():
+    # +-Inf has no fixed-point image: the qfx specification (oracle modes 1, 2) and the CUDA fast / SQL modes refuse it
+    # alike; the literal mode runs the reference's arithmetic on it (NaN statistics and all)
+    ids, rows = ds.unit_gaussian(3000, 8, seed=21)
+    rows = rows.copy()
+    rows[17, 3] = np.float32(np.inf)
+    rows[900, 5] = np.float32(-np.inf)
+    for omode in (oracle.MODE_QFX, oracle.MODE_SQL):
+        with pytest.raises(ValueError):
+            oracle.build(ids, rows, omode)
+    with vi.Context(0) as ctx:
+        ctx.reserve(len(ids), 8)
+        ctx.add(ids, rows)
+        for mode in (vi.MODE_FAST, vi.MODE_SQL):
+            with pytest.raises(ValueError, match="Inf"):
+                ctx.build(mode)
+    assert_same_table(ids, rows, vi.MODE_EXACT)
+    one_ids, one_rows = ids[:1], np.full((1, 8), np.inf, np.float32)   # a single point is a leaf whatever its value
+    assert_same_table(one_ids, one_rows, vi.MODE_FAST)

@@ -444,11 +444,15 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   env.gstride = (size_t)ctx->ld * 3 + 3;
 }
 
+// +-Inf has no fixed-point image (xi would saturate and the 64-bit partial sums of xi^2 overflow): the fast / SQL modes
+// refuse it, as their CPU statement does; VI_MODE_EXACT takes any float
+static const char* const kInfMessage =
+    "fast / SQL mode: the data contains +-Inf, which has no fixed-point image; use VI_MODE_EXACT";
+
 static void set_q_exponent(vi_ctx* ctx, BuildEnv& env, float amax)
 {
   int qe = 0;
-  if (isinf(amax)) qe = 128;
-  else if (amax > 0.f) (void)frexpf(amax, &qe);
+  if (amax > 0.f) (void)frexpf(amax, &qe);
   if (qe < -96) qe = -96;
   if (qe > 128) qe = 128;
   env.qk = ldexpf(1.0f, VI_QBITS - qe);
@@ -986,6 +990,7 @@ static int build_single(vi_ctx* ctx, BuildEnv& env)
     float amax = 0.f;
     rc = local_absmax(ctx, ctx->rows, ctx->n, env, &amax);
     if (rc != VI_OK) return rc;
+    if (isinf(amax)) return ctx->fail(VI_ERR_INVALID_ARG, kInfMessage);
     set_q_exponent(ctx, env, amax);
   }
   k_init_level0<<<(n + 255) / 256, 256, 0, st>>>(ctx->perm[0], ctx->pid[0], ctx->ids, ctx->seg_of[0], n, ctx->seg[0],
@@ -1106,6 +1111,7 @@ static int build_sharded_try(vi_ctx* ctx, BuildEnv& env, int Lcap, int* retry_le
   }
   float amax = 0.f;
   memcpy(&amax, &amax_bits, 4);
+  if (isinf(amax)) return ctx->fail(VI_ERR_INVALID_ARG, kInfMessage);  // the same on every rank (all-reduced maximum)
   set_q_exponent(ctx, env, amax);
   if (nglobal >= 0x7fffffffull) return ctx->fail(VI_ERR_CAPACITY, "more than 2^31-2 points");
   if (nglobal == 0) return finish_table(ctx, env, 0, ev_begin, nullptr);
