@@ -712,7 +712,9 @@ def main():
         log(f"exact e2e: {xe:.1f} ms/step")
         ctx.build(vi.MODE_FAST)
     if not args.no_search:
-        # search through the plugin call with HOST buffers: queries H2D, traversal (count + fill), offsets and ids D2H
+        # search through the plugin call with HOST buffers: queries H2D, traversal, offsets and ids D2H.  Two figures per
+        # proximity: pageable numpy buffers allocated inside the call (what a casual caller does), and the steady state
+        # of a serving loop -- pinned buffers owned by the caller, sized by a first call (which also sizes the pool)
         rng = np.random.default_rng(77)
         se = {}
         for p, nqe in ((0.0, min(args.queries, 1_000_000)), (0.01, min(args.queries, 200_000))):
@@ -724,10 +726,25 @@ def main():
             t0 = time.perf_counter()
             offs, out = ctx.search(qh, p)
             dt = (time.perf_counter() - t0) * 1e3
-            se[f"p={p}"] = {"queries_per_sec": nqe / (dt / 1e3), "ms": dt, "queries": nqe, "candidates": int(len(out)),
+            q_pin = torch.empty(qh.shape, dtype=torch.float32, pin_memory=True).numpy()
+            q_pin[:] = qh
+            o_pin = torch.empty(nqe + 1, dtype=torch.int64, pin_memory=True).numpy()
+            i_pin = torch.empty(max(len(out), 1), dtype=torch.int64, pin_memory=True).numpy()
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                tot = ctx.search_begin(q_pin, p)
+                ctx.search_fetch(o_pin, i_pin)
+                dp = (time.perf_counter() - t0) * 1e3
+                best = dp if best is None else min(best, dp)
+            assert tot == len(out) and np.array_equal(o_pin, offs) and np.array_equal(i_pin[:tot], out)
+            se[f"p={p}"] = {"queries_per_sec": nqe / (best / 1e3), "ms": best, "queries": nqe, "candidates": int(len(out)),
                             "h2d_bytes": int(qh.nbytes), "d2h_bytes": int(offs.nbytes + out.nbytes),
-                            "path": "vi_search_begin + vi_search_fetch, pageable host buffers"}
-            log(f"search e2e p={p}: {dt:.1f} ms for {nqe} queries, {len(out)} candidates")
+                            "path": "vi_search_begin + vi_search_fetch, caller-owned pinned host buffers (best of 3)",
+                            "pageable_first_call": {"queries_per_sec": nqe / (dt / 1e3), "ms": dt,
+                                                    "path": "the same with numpy buffers allocated inside the call"}}
+            log(f"search e2e p={p}: {best:.1f} ms pinned / {dt:.1f} ms pageable for {nqe} queries, {len(out)} candidates")
+            del q_pin, o_pin, i_pin
         result.setdefault("search", {})["e2e"] = se
     if args.topk > 0:
         # quality layer: k nearest candidates vs exact k-NN

@@ -358,6 +358,18 @@ class Context:
         self._check(self._L.vi_search_fetch(self._h, _p(offsets, _i64p), _p(ids, _i64p), ids.shape[0]))
         return offsets, ids[:total.value]
 
+    def search_begin(self, queries: np.ndarray, proximity: float) -> int:
+        """vi_search_begin: stages the queries, walks the table, returns the number of candidates."""
+        queries = np.ascontiguousarray(queries, np.float32)
+        nq, d = queries.shape
+        total = ctypes.c_int64(0)
+        self._check(self._L.vi_search_begin(self._h, _p(queries, _f32p), nq, d, ctypes.c_float(proximity), ctypes.byref(total)))
+        return total.value
+
+    def search_fetch(self, offsets: np.ndarray, ids: np.ndarray):
+        """vi_search_fetch into caller-owned (e.g. pinned) arrays: offsets[nq+1], ids[>= total]."""
+        self._check(self._L.vi_search_fetch(self._h, _p(offsets, _i64p), _p(ids, _i64p), ids.shape[0]))
+
     def search_two_call(self, queries: np.ndarray, proximity: float):
         """The size-then-fill protocol of vi_search itself (ids == NULL first, then cap >= total)."""
         queries = np.ascontiguousarray(queries, np.float32)
