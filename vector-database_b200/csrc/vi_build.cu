@@ -344,6 +344,7 @@ struct BuildEnv
   int sql;      // dbo.BuildIndex's rules (DDL.sql:44-202): level_mx()
   u32 t_team, t_big, big_unroll;
   u32 t_slot;   // ranges of >= t_slot points get a big-list slot (their sums can be kept / derived); t_slot <= t_big
+  u32 ring;     // warp-per-range kernel: rows through the bulk-async shared-memory ring (vi_stats_fast.cuh RING)
   u32 sibling;  // fast mode: sum only the smaller child of a big pair, derive the other from the parent (1 = on)
   u32 t_sub;    // ranges of 2..t_sub points are finished by the sub-tree kernel (0 = off)
   u32 sub_minb;
@@ -407,6 +408,7 @@ static void env_init(vi_ctx* ctx, BuildEnv& env, int mode)
   env.t_big = mode == VI_MODE_FAST ? t_big_fast : t_big_exact;
   env.big_unroll = env_u32("VI_B200_BIG_UNROLL", 8, 0, 8);  // 0 = cp.async ring
   env.sibling = env_u32("VI_B200_SIBLING", 1, 0, 1);
+  env.ring = env_u32("VI_B200_RING", 0, 0, 1);
   // sibling derivation reaches below the chunked class: a warp-per-range range of >= t_slot points keeps its sums when
   // its children may pair up, and the larger child of such a pair is derived instead of summed
   env.t_slot = (mode == VI_MODE_FAST && env.sibling) ? std::min(env.t_big, env_u32("VI_B200_T_SLOT", 128, VI_MIN_BIG, 1u << 30))
@@ -707,12 +709,35 @@ static int enqueue_level(vi_ctx* ctx, BuildEnv& env, const LevelState& b, int le
     if (may_warp)
     {
       u64* wg = (env.sibling && b.nbig) ? gacc_cur : nullptr;
+      const u32 wgrid = (u32)(((u64)b.R * 32 + 255) / 256);
+      if (env.ring && shp.ts == 8 && shp.full)
+      {
+        // rows through the bulk-async shared-memory ring (vi_stats_fast.cuh RING)
+        const size_t rsm = 8 * ring_smem_bytes_per_warp(ld);
+#define CALL_RING(CH)                                                                                                  \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    VI_CUDA_TRY(cudaFuncSetAttribute(k_stats_small_fast<8, CH, true, true, true>,                                      \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));                          \
+    k_stats_small_fast<8, CH, true, true, true><<<wgrid, 256, rsm, st>>>(                                              \
+        lvp, sg, wlo, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout, wg,            \
+        ctx->bl_parent[cur], ctx->bl_sib[cur], 2 * t_slot);                                                            \
+  } while (0)
+        if (shp.ch == 1) CALL_RING(1);
+        else if (shp.ch == 2) CALL_RING(2);
+        else if (shp.ch == 3) CALL_RING(3);
+        else CALL_RING(4);
+#undef CALL_RING
+      }
+      else
+      {
 #define CALL_WARP(TS, CH, FULL)                                                                              \
-  k_stats_small_fast<TS, CH, FULL, true><<<(u32)(((u64)b.R * 32 + 255) / 256), 256, 0, st>>>(                 \
+  k_stats_small_fast<TS, CH, FULL, true><<<wgrid, 256, 0, st>>>(                                              \
       lvp, sg, wlo, t_big, ctx->perm[cur], ctx->pid[cur], rows, ld, dims, env.qk, env.qinv, mx, sout, wg,      \
       ctx->bl_parent[cur], ctx->bl_sib[cur], 2 * t_slot)
-      FAST_DISPATCH(shp, CALL_WARP);
+        FAST_DISPATCH(shp, CALL_WARP);
 #undef CALL_WARP
+      }
       ++env.launches;
     }
     if (b.nbig)

@@ -109,8 +109,55 @@ __device__ __forceinline__ float qfx_mid(i64 s1, u32 n, double qinv)
   return __double2float_rn(__dmul_rn(__ddiv_rn(__ll2double_rn(s1), (double)n), qinv));
 }
 
-template <int TS, int CH, bool FULL, bool WPS>
-__global__ void __launch_bounds__(256, (CH == 1) ? 4 : ((TS * CH <= 32) ? 3 : 1))
+// ---- bulk-async row ring of the warp-per-range kernel (RING) -----------------------------------------------------------
+// The warp class (33 .. 511 points per range, levels 13-18 of 10M x 96) is latency-bound: a lane that fetches its
+// share of a row into registers keeps 2 rows in flight (80 registers, profiles/r1_ncu_final.md).  With RING every row
+// is ONE 1-D bulk copy (cp.async.bulk, the TMA engine without a tensor map: 384 contiguous bytes at D = 96) into a
+// 32-slot shared-memory ring owned by the warp, completion on one mbarrier per slot (expect_tx = row bytes): the lane
+// that holds a row's index issues its copy, 32 rows stay in flight per warp without holding a register, and the teams
+// read their rows with LDS.128.  A slot is refilled with the row 32 positions further on as soon as the four teams have
+// read the four rows of a step (__syncwarp), so the ring never drains inside a range.
+constexpr int RING_SLOTS = 32;
+
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(u32 bar, u32 parity)
+{
+  u32 ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity)
+{
+  u32 spins = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 24)) __trap();  // a copy that never lands is a bug: fail the launch instead of hanging the GPU
+}
+
+__host__ __device__ inline size_t ring_smem_bytes_per_warp(int ld) { return (size_t)RING_SLOTS * (size_t)ld * 4 + RING_SLOTS * 8; }
+
+template <int TS, int CH, bool FULL, bool WPS, bool RING = false>
+__global__ void __launch_bounds__(256, (CH == 1) ? 4 : ((TS * CH <= 32) ? (RING ? 2 : 3) : 1))
 k_stats_small_fast(const LevelDev* __restrict__ lvp, SegLevel sg, u32 nmin, u32 nmax, const u32* __restrict__ perm,
                    const i64* __restrict__ pid, const float* __restrict__ rows, int ld, int dims, float qk, double qinv, int mx,
                    StatsOut out, u64* __restrict__ gacc, const u32* __restrict__ bl_parent, const u32* __restrict__ bl_sib,
@@ -160,6 +207,53 @@ k_stats_small_fast(const LevelDev* __restrict__ lvp, SegLevel sg, u32 nmin, u32 
     for (int i = 0; i < CH * 4; ++i) { s1[i] = 0; s2[i] = 0; }
 
     u32 mine = (gl < n) ? pp[gl] : 0u;
+    if constexpr (RING)
+    {
+      static_assert(!RING || (WPS && FULL && TS == 8), "the ring serves the warp-per-range kernel on rows of 8 * CH float4");
+      extern __shared__ __align__(16) unsigned char ring_smem[];
+      const u32 rowbytes = (u32)ld * 4u;
+      unsigned char* wbase = ring_smem + (size_t)(threadIdx.x >> 5) * ring_smem_bytes_per_warp(ld);
+      const u32 slot0 = (u32)__cvta_generic_to_shared(wbase);
+      const u32 bar0 = slot0 + RING_SLOTS * rowbytes;
+      mbar_init(bar0 + (u32)lane * 8u, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      u32 nxt = (32u + (u32)lane < n) ? pp[32 + lane] : 0u;  // row indexes one and two blocks ahead
+      if ((u32)lane < n)
+      {
+        mbar_expect_tx(bar0 + (u32)lane * 8u, rowbytes);
+        bulk_g2s(slot0 + (u32)lane * rowbytes, rows + (size_t)mine * ld, rowbytes, bar0 + (u32)lane * 8u);
+      }
+      for (u32 jb = 0; jb < n; jb += 32)
+      {
+        const u32 nxt2 = (jb + 64u + (u32)lane < n) ? pp[jb + 64 + lane] : 0u;
+        const u32 m = min(32u, n - jb);
+        const u32 par = (jb >> 5) & 1u;
+        for (u32 j0 = 0; j0 < m; j0 += 4)
+        {
+          const u32 jj = j0 + (u32)trow;
+          if (jj < m)
+          {
+            mbar_wait(bar0 + jj * 8u, par);
+            const float4* sp = reinterpret_cast<const float4*>(wbase + (size_t)jj * rowbytes);
+            float4 x[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) x[k] = sp[k * TS + tl];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) qfx_acc4(s1 + k * 4, s2 + k * 4, x[k], qk);
+          }
+          __syncwarp();  // the four rows of this step have been read (and used) by their teams: their slots are free
+          if ((u32)lane >= j0 && (u32)lane < j0 + 4u && jb + 32u + (u32)lane < n)
+          {
+            mbar_expect_tx(bar0 + (u32)lane * 8u, rowbytes);
+            bulk_g2s(slot0 + (u32)lane * rowbytes, rows + (size_t)nxt * ld, rowbytes, bar0 + (u32)lane * 8u);
+          }
+        }
+        nxt = nxt2;
+      }
+    }
+    else
     for (u32 jb = 0; jb < n; jb += GS)
     {
       const u32 nxt = (jb + GS + gl < n) ? pp[jb + GS + gl] : 0u;  // prefetch the next block of row indexes
