@@ -197,8 +197,11 @@ int vi_search_topk(vi_ctx* ctx, const float* queries, int64_t nq, int32_t dims, 
                    int64_t* ids, float* dist, int32_t* count, int64_t* candidates);
 
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------------------------------------ */
-/* A multi-rank vi_build (VI_MODE_FAST only: its integer sums are order-independent) treats the points added to the
- * `world` contexts as ONE data set in rank order (rank 0's points first).  Top levels: every rank reduces its local
+/* A multi-rank vi_build treats the points added to the `world` contexts as ONE data set in rank order (rank 0's points
+ * first).  VI_MODE_EXACT (the chains of the literal recurrence run over the global order and cannot be split): every rank
+ * receives all points (one all-gather), builds the levels above ceil(log2 world) redundantly -- same kernels, same data,
+ * same bits, no communication -- and finishes only the sub-trees of the ranges it owns; the contexts end up in the same
+ * shape as below.  VI_MODE_FAST / VI_MODE_SQL (integer sums, order-independent):  Top levels: every rank reduces its local
  * slice of every range and the sums meet in one all-reduce per level; then each range of level L = ceil(log2 world)+1
  * moves to one owner rank (a single all-to-all) and the owners finish their sub-trees without communication.  After
  * the build a context holds the rows of the shared top levels (replicated) plus the rows of the sub-trees it owns;

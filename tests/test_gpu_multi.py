@@ -1,5 +1,6 @@
-"""GPU, one process per GPU over NCCL: the sharded fast-mode build (vi_build.cu build_sharded) must give, as the
-union of the per-rank tables, exactly the single-rank oracle table.  Needs >= 2 GPUs (skipped otherwise)."""
+"""GPU, one process per GPU over NCCL: the multi-rank builds (vi_build.cu build_sharded: fast / SQL mode with shared
+levels + ownership exchange; build_sharded_exact: replicated points, common top, owned sub-trees) must give, as the union
+of the per-rank tables, exactly the single-rank oracle table.  Needs >= 2 GPUs (skipped otherwise)."""
 import os
 import sys
 
@@ -17,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 def _data(n, d, seed, kind):
     from vectorindex import synthetic as ds
-    ids, rows = getattr(ds, "unit_gaussian" if kind == "sql_dups" else "uniform" if kind == "clustered" else kind)(n, d, seed=seed)
+    ids, rows = getattr(ds, "unit_gaussian" if kind in ("sql_dups", "exact") else "uniform" if kind == "clustered" else kind)(n, d, seed=seed)
     ids = ids * 3 + 7
     if kind == "clustered":
         # a tight cluster (|x| ~ 1e-7) plus outliers that set the quantisation scale: below the root the ranges are
@@ -41,7 +42,7 @@ def _worker(rank, world, port, q, n, d, seed, kind, transport="nccl"):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     ids, rows = _data(n, d, seed, kind)
-    mode = vi.MODE_SQL if kind == "sql_dups" else vi.MODE_FAST
+    mode = vi.MODE_SQL if kind == "sql_dups" else vi.MODE_EXACT if kind == "exact" else vi.MODE_FAST
     lo, hi = rank * n // world, (rank + 1) * n // world
     if kind == "uniform" and rank == world - 1:
         lo = hi = n  # an empty shard on the last rank ...
@@ -84,7 +85,8 @@ def _worker(rank, world, port, q, n, d, seed, kind, transport="nccl"):
 @pytest.mark.parametrize("n,d,seed,kind,transport", [(200_000, 96, 3, "unit_gaussian", "nccl"), (5000, 16, 5, "uniform", "nccl"),
                                                      (30_000, 24, 7, "unit_gaussian", "callbacks"),
                                                      (20_000, 8, 9, "clustered", "nccl"),
-                                                     (60_000, 12, 11, "sql_dups", "nccl")])
+                                                     (60_000, 12, 11, "sql_dups", "nccl"),
+                                                     (150_000, 24, 13, "exact", "nccl"), (9000, 40, 15, "exact", "callbacks")])
 def test_sharded_build_equals_oracle(world, n, d, seed, kind, transport):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -109,7 +111,10 @@ def test_sharded_build_equals_oracle(world, n, d, seed, kind, transport):
     owned_rows = []
     for r in range(world):
         rid, dim, mid, oid, shared, calls, levels, full = res[r]
-        assert calls["alltoallv"] >= 2  # rows + ids, once per attempt
+        if kind == "exact":
+            assert calls["allgather"] >= 2 or transport == "callbacks"  # every rank receives every point: rows + ids
+        else:
+            assert calls["alltoallv"] >= 2  # rows + ids, once per attempt
         if kind == "clustered":
             assert calls["retry"] == 1
         for k in range(len(rid)):
@@ -123,7 +128,7 @@ def test_sharded_build_equals_oracle(world, n, d, seed, kind, transport):
                 union[int(rid[k])] = val
         owned_rows.append(len(rid) - shared)
     ids, rows = _data(n, d, seed, kind)
-    ref = oracle.build(ids, rows, oracle.MODE_SQL if kind == "sql_dups" else oracle.MODE_QFX)
+    ref = oracle.build(ids, rows, oracle.MODE_SQL if kind == "sql_dups" else oracle.MODE_LITERAL if kind == "exact" else oracle.MODE_QFX)
     if kind == "sql_dups":
         assert (ref.dimension == -3).any()
     want = {int(r): (int(dm), int(np.float32(m).view(np.uint32)), int(i))

@@ -229,8 +229,6 @@ int vi_build(vi_ctx* ctx, int32_t mode, vi_build_info* info)
   if (mode != VI_MODE_EXACT && mode != VI_MODE_FAST && mode != VI_MODE_SQL)
     return ctx->fail(VI_ERR_INVALID_ARG, "unknown build mode");
   if (ctx->dims == 0) return ctx->fail(VI_ERR_STATE, "no points: vi_points_reserve / vi_points_add first");
-  if (ctx->world > 1 && mode == VI_MODE_EXACT)
-    return ctx->fail(VI_ERR_INVALID_ARG, "multi-rank build needs VI_MODE_FAST or VI_MODE_SQL (order-independent sums)");
   VI_CUDA_TRY(cudaSetDevice(ctx->device));
   ctx->pending_nq = -1;
   int rc = vi_build_impl(ctx, mode);
@@ -248,8 +246,6 @@ int vi_build_copy(vi_ctx* ctx, int32_t mode, vi_build_info* info, int64_t* range
   if (mode != VI_MODE_EXACT && mode != VI_MODE_FAST && mode != VI_MODE_SQL)
     return ctx->fail(VI_ERR_INVALID_ARG, "unknown build mode");
   if (ctx->dims == 0) return ctx->fail(VI_ERR_STATE, "no points: vi_points_reserve / vi_points_add first");
-  if (ctx->world > 1 && mode == VI_MODE_EXACT)
-    return ctx->fail(VI_ERR_INVALID_ARG, "multi-rank build needs VI_MODE_FAST or VI_MODE_SQL (order-independent sums)");
   VI_CUDA_TRY(cudaSetDevice(ctx->device));
   ctx->pending_nq = -1;
   ctx->out = vi_ctx::CopyOut();

@@ -861,7 +861,9 @@ static int enqueue_level(vi_ctx* ctx, BuildEnv& env, const LevelState& b, int le
 // The level loop: processes seg[s.cur] (ranges of depth s.level) until no range with >= 2 points is left.
 // `rows` is the row store perm[] indexes.  `s` is the exact state of the first level; on return it holds the
 // final row / sub-tree cursors.
-static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* rows)
+// stop_level >= 0: return before enqueuing that level, `s` = its exact state (the exact-mode multi-rank build filters the
+// ranges there and calls again).
+static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* rows, int stop_level = -1)
 {
   cudaStream_t st = ctx->stream;
   const int mode = env.mode;
@@ -927,6 +929,7 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
     while (known.level + (lag - 1) < level)
       if ((rc = absorb()) != VI_OK) return rc;
     if (known.R == 0) break;  // nothing open at known.level: every level already enqueued behind it is a no-op
+    if (stop_level >= 0 && level >= stop_level) break;
     if (level >= VI_MAX_DEPTH)
     {
       // splitting a depth-62 range overflows rangeId: make sure such a range really exists before failing
@@ -957,6 +960,15 @@ static int run_levels(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* ro
   }
   while (known.level < level)
     if ((rc = absorb()) != VI_OK) return rc;
+  if (stop_level >= 0 && known.level == stop_level && known.R > 0)
+  {
+    // stopped in front of an open level: hand its exact record back
+    const int keep_cur = cur;
+    s = known;
+    s.cur = keep_cur;
+    s.level = known.level;
+    return VI_OK;
+  }
   s.A = 0;
   s.R = 0;
   s.row_next = known.row_next;
@@ -1404,8 +1416,210 @@ static int build_sharded_try(vi_ctx* ctx, BuildEnv& env, int Lcap, int* retry_le
   return finish_table(ctx, env, s.row_next, ev_begin, ctx->own_n > 0 ? ctx->own_rows : ctx->rows);
 }
 
+// ---- multi-rank build, exact mode --------------------------------------------------------------
+// The literal recurrence is one sequential chain per (range, dimension) over the GLOBAL stable order: the top levels
+// cannot be split over ranks.  So every rank first receives all points (one all-gather-v in rank order = global order),
+// builds the levels 0 .. L-1, L = ceil(log2 G), redundantly -- the same deterministic kernels on the same data give the same
+// bits everywhere, no communication -- and then keeps only the level-L ranges it owns (largest first to the least loaded
+// rank, as the fast mode) and finishes their sub-trees alone.  What the ranks end up with has the fast mode's shape:
+// rows [0, shared_rows) numbered while the ranges were common (a level-L range's row is filled in by its owner, a
+// Dimension = -2 placeholder elsewhere), local rows behind them; vi_table_replicate works unchanged.  Gain: only the
+// levels below L divide by G (levels 0-2 are 260 of the 342 ms of a 10M x 96 build).
+__global__ void k_owned_filter(const SegLevel sg, const u32* __restrict__ seg_of, const u32* __restrict__ perm,
+                               const i64* __restrict__ pid, u32 A, const u32* __restrict__ new_seg /* [R] or VI_NONE */,
+                               const u32* __restrict__ shift /* [R] positions removed before the range */,
+                               u32* __restrict__ perm2, i64* __restrict__ pid2, u32* __restrict__ seg_of2)
+{
+  const u32 p = blockIdx.x * 256u + threadIdx.x;
+  if (p >= A) return;
+  const u32 s = seg_of[p];
+  const u32 ns = new_seg[s];
+  if (ns == VI_NONE) return;
+  const u32 q = p - shift[s];
+  perm2[q] = perm[p];
+  pid2[q] = pid[p];
+  seg_of2[q] = ns;
+}
+
+static int build_sharded_exact(vi_ctx* ctx, BuildEnv& env)
+{
+  cudaStream_t st = ctx->stream;
+  const int G = ctx->world, me = ctx->rank;
+  const int ld = ctx->ld;
+  cudaEvent_t ev_begin = env_event(ctx, env);
+  if (!ctx->sh_dev)
+  {
+    VI_CUDA_TRY(cudaMalloc(&ctx->sh_dev, sizeof(ShDev)));
+    VI_CUDA_TRY(cudaMallocHost(&ctx->sh_host, sizeof(ShHost)));
+  }
+  ShDev* sd = (ShDev*)ctx->sh_dev;
+  ShHost* shh = (ShHost*)ctx->sh_host;
+  // ---- every rank gets every point, in rank order ----------------------------------------------------------------------
+  const u64 nloc = (u64)ctx->n;
+  VI_CUDA_TRY(cudaMemsetAsync(sd->v0, 0, sizeof(sd->v0), st));
+  VI_CUDA_TRY(cudaMemcpyAsync(sd->v0 + me, &nloc, 8, cudaMemcpyHostToDevice, st));
+  int rc = vi_coll_allreduce_u64(ctx, sd->v0, G);
+  if (rc != VI_OK) return rc;
+  VI_CUDA_TRY(cudaMemcpyAsync(shh->v0, sd->v0, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaStreamSynchronize(st));
+  u64 N = 0, my_off = 0;
+  std::vector<int64_t> off_r(G), len_r(G), off_i(G), len_i(G);
+  for (int g = 0; g < G; ++g)
+  {
+    if (g == me) my_off = N;
+    off_r[g] = (int64_t)N * ld * 4;
+    len_r[g] = (int64_t)shh->v0[g] * ld * 4;
+    off_i[g] = (int64_t)N * 8;
+    len_i[g] = (int64_t)shh->v0[g] * 8;
+    N += shh->v0[g];
+  }
+  if (N >= 0x7fffffffull) return ctx->fail(VI_ERR_CAPACITY, "more than 2^31-2 points");
+  if (N == 0) return finish_table(ctx, env, 0, ev_begin, nullptr);
+  if ((int64_t)N > ctx->own_cap)
+  {
+    cudaFree(ctx->own_rows); cudaFree(ctx->own_ids);
+    ctx->own_rows = nullptr; ctx->own_ids = nullptr; ctx->own_cap = 0;
+    VI_CUDA_TRY(cudaMalloc((void**)&ctx->own_rows, ((size_t)N + 64) * ld * sizeof(float)));
+    VI_CUDA_TRY(cudaMalloc((void**)&ctx->own_ids, ((size_t)N + 64) * sizeof(i64)));
+    ctx->own_cap = (int64_t)N;
+  }
+  if (nloc)
+  {
+    VI_CUDA_TRY(cudaMemcpyAsync(ctx->own_rows + my_off * ld, ctx->rows, (size_t)nloc * ld * 4, cudaMemcpyDeviceToDevice, st));
+    VI_CUDA_TRY(cudaMemcpyAsync(ctx->own_ids + my_off, ctx->ids, (size_t)nloc * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  if ((rc = vi_coll_allgatherv_inplace(ctx, ctx->own_rows, off_r.data(), len_r.data()))) return rc;
+  if ((rc = vi_coll_allgatherv_inplace(ctx, ctx->own_ids, off_i.data(), len_i.data()))) return rc;
+  ctx->own_n = (int64_t)N;
+  const float* rows = ctx->own_rows;
+  const u32 n = (u32)N;
+  rc = grow_table(ctx, (int64_t)(2 * N + N / 8 + 1024), 0);
+  if (rc != VI_OK) return rc;
+  if (n == 1)
+  {
+    k_single_point<<<1, 1, 0, st>>>(ctx->own_ids, ctx->t_rid, ctx->t_dim, ctx->t_mid, ctx->t_id, ctx->t_low, ctx->t_high,
+                                    ctx->t_src);
+    ++env.launches;
+    ctx->shared_rows = 1;
+    return finish_table(ctx, env, 1, ev_begin, rows);
+  }
+  rc = alloc_workspace(ctx, (int64_t)N);
+  if (rc != VI_OK) return rc;
+  // ---- the common top: levels 0 .. L-1, the same on every rank ----------------------------------------------------------
+  int L = 1;
+  while ((1 << L) < G) ++L;  // stop in front of level L = ceil(log2 G): 2^L >= G ranges (mean splits are near halves)
+  k_init_level0<<<(n + 255) / 256, 256, 0, st>>>(ctx->perm[0], ctx->pid[0], ctx->own_ids, ctx->seg_of[0], n, ctx->seg[0],
+                                                 ctx->big_list[0], ctx->t_rid, ctx->t_low, ctx->t_high);
+  ++env.launches;
+  LevelState s{};
+  s.A = n;
+  s.R = 1;
+  s.nbig = n >= env.t_big ? 1u : 0u;
+  s.chunks = 0;
+  s.minseg = n;
+  s.maxseg = n;
+  s.row_next = 1;
+  s.cur = 0;
+  s.level = 0;
+  rc = run_levels(ctx, env, s, rows, L);
+  if (rc != VI_OK) return rc;
+  if (s.R == 0)
+  {
+    // the whole tree fitted in the common levels: every rank holds all of it
+    ctx->shared_rows = s.row_next;
+    return finish_table(ctx, env, s.row_next, ev_begin, rows);
+  }
+  // ---- ownership of the level-L ranges, then the rest alone --------------------------------------------------------
+  const u32 R = s.R, T = s.row_next;
+  if (R > (u32)VI_SH_MAXR * 2) return ctx->fail(VI_ERR_STATE, "too many ranges at the ownership level");
+  std::vector<u32> cnt(R), start(R), rowi(R);
+  std::vector<i64> rid(R);
+  SegLevel& sg = ctx->seg[s.cur];
+  VI_CUDA_TRY(cudaMemcpyAsync(cnt.data(), sg.count, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaMemcpyAsync(start.data(), sg.start, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaMemcpyAsync(rowi.data(), sg.row, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaMemcpyAsync(rid.data(), sg.rid, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
+  VI_CUDA_TRY(cudaStreamSynchronize(st));
+  std::vector<u32> order(R), owner(R);
+  for (u32 i = 0; i < R; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return cnt[a] > cnt[b]; });
+  std::vector<u64> load(G, 0);
+  for (u32 i : order)
+  {
+    int best = 0;
+    for (int g = 1; g < G; ++g)
+      if (load[g] < load[best]) best = g;
+    owner[i] = (u32)best;
+    load[best] += cnt[i];
+  }
+  std::vector<u32> new_seg(R, VI_NONE), shift(R, 0), placeholders, f_start, f_count, f_row, f_big;
+  std::vector<i64> f_rid;
+  u32 removed = 0, pos = 0, minseg = 0xffffffffu, maxseg = 0;
+  for (u32 i = 0; i < R; ++i)  // ranges are contiguous position slices in index order
+  {
+    if (owner[i] != (u32)me)
+    {
+      removed += cnt[i];
+      placeholders.push_back(rowi[i]);
+      continue;
+    }
+    new_seg[i] = (u32)f_start.size();
+    shift[i] = removed;
+    if (cnt[i] >= env.t_big) f_big.push_back((u32)f_start.size());
+    f_start.push_back(pos);
+    f_count.push_back(cnt[i]);
+    f_row.push_back(rowi[i]);
+    f_rid.push_back(rid[i]);
+    pos += cnt[i];
+    minseg = std::min(minseg, cnt[i]);
+    maxseg = std::max(maxseg, cnt[i]);
+  }
+  Blob blob;
+  const size_t o_ns = blob.add(new_seg), o_sh = blob.add(shift), o_ph = blob.add(placeholders), o_fs = blob.add(f_start),
+               o_fc = blob.add(f_count), o_fr = blob.add(f_row), o_fb = blob.add(f_big), o_rid = blob.add(f_rid);
+  if (blob.bytes.size() > VI_SH_STAGE) return ctx->fail(VI_ERR_CAPACITY, "ownership tables too large");
+  memcpy(shh->tables, blob.bytes.data(), blob.bytes.size());
+  VI_CUDA_TRY(cudaMemcpyAsync(sd->tables, shh->tables, blob.bytes.size(), cudaMemcpyHostToDevice, st));
+  auto dptr = [&](size_t o) { return sd->tables + o; };
+  if (!placeholders.empty())
+  {
+    k_sh_placeholders<<<((u32)placeholders.size() + 255) / 256, 256, 0, st>>>((const u32*)dptr(o_ph), (u32)placeholders.size(),
+                                                                              ctx->t_dim);
+    ++env.launches;
+  }
+  ctx->shared_rows = T;
+  LevelState f{};
+  f.row_next = T;
+  f.level = s.level;
+  f.cur = s.cur ^ 1;  // the filtered level goes to the other half of the ping-pong
+  f.A = pos;
+  f.R = (u32)f_start.size();
+  f.nbig = (u32)f_big.size();
+  f.chunks = 0;
+  f.minseg = minseg;
+  f.maxseg = maxseg;
+  if (f.R > 0)
+  {
+    k_owned_filter<<<(s.A + 255) / 256, 256, 0, st>>>(sg, ctx->seg_of[s.cur], ctx->perm[s.cur], ctx->pid[s.cur], s.A,
+                                                      (const u32*)dptr(o_ns), (const u32*)dptr(o_sh), ctx->perm[f.cur],
+                                                      ctx->pid[f.cur], ctx->seg_of[f.cur]);
+    ++env.launches;
+    SegLevel& d = ctx->seg[f.cur];
+    const size_t r4 = (size_t)f.R * 4;
+    VI_CUDA_TRY(cudaMemcpyAsync(d.start, dptr(o_fs), r4, cudaMemcpyDeviceToDevice, st));
+    VI_CUDA_TRY(cudaMemcpyAsync(d.count, dptr(o_fc), r4, cudaMemcpyDeviceToDevice, st));
+    VI_CUDA_TRY(cudaMemcpyAsync(d.row, dptr(o_fr), r4, cudaMemcpyDeviceToDevice, st));
+    VI_CUDA_TRY(cudaMemcpyAsync(d.rid, dptr(o_rid), (size_t)f.R * 8, cudaMemcpyDeviceToDevice, st));
+    if (f.nbig) VI_CUDA_TRY(cudaMemcpyAsync(ctx->big_list[f.cur], dptr(o_fb), (size_t)f.nbig * 4, cudaMemcpyDeviceToDevice, st));
+    rc = run_levels(ctx, env, f, rows);
+    if (rc != VI_OK) return rc;
+  }
+  return finish_table(ctx, env, f.row_next, ev_begin, rows);
+}
+
 static int build_sharded(vi_ctx* ctx, BuildEnv& env)
 {
+  if (env.mode == VI_MODE_EXACT) return build_sharded_exact(ctx, env);
   int Lcap = 64;
   for (;;)
   {
