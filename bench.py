@@ -427,6 +427,28 @@ def run_multi(args, rank, world, local):
     d2h = torch.tensor([float(k_rows) * 24], device=dev, dtype=torch.float64)
     dist.all_reduce(d2h, op=dist.ReduceOp.SUM)
     e2e = float(te.item())
+    # ---- exact mode over the same shards: points all-gathered, common top levels, owned sub-trees -----------
+    exact = None
+    if not args.no_exact:
+        ctx.build(vi.MODE_EXACT)
+        sync_all()
+        xa = torch.cuda.Event(enable_timing=True)
+        xb = torch.cuda.Event(enable_timing=True)
+        xa.record(stream)
+        for _ in range(2):
+            xinfo = ctx.build(vi.MODE_EXACT)
+        xb.record(stream)
+        sync_all()
+        tx = torch.tensor([xa.elapsed_time(xb) / 2], device=dev, dtype=torch.float64)
+        dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        ctx.replicate()
+        sync_all()
+        if rank == 0:
+            exact = {"value": n / (float(tx.item()) / 1e3), "unit": "vectors/s", "ms_per_step": float(tx.item()), "steps": 2,
+                     "warmup": 1, "table_checksum": table_checksum(*ctx.ranges()), "shared_rows": int(ctx.shared_rows),
+                     "note": "literal float32 Welford, bit-identical table; every rank holds all points and builds the levels "
+                             "above ceil(log2 G) redundantly (sequential chains over the global order cannot shard), then "
+                             "finishes the sub-trees it owns"}
     if rank == 0:
         result = {"metric": "index_build_vectors_per_sec", "value": n / (ms_per_step / 1e3), "unit": "vectors/s",
                   "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -451,7 +473,7 @@ def run_multi(args, rank, world, local):
                           "h2d_bytes_per_step": n * (4 * DIMS + 8), "d2h_bytes_per_step": int(d2h.item()),
                           "steps": len(e2e_ms), "warmup": 2, "rank0_ms_before_the_closing_barrier": sum(own_ms) / len(own_ms),
                           "path": "per rank: vi_points_reserve + vi_points_add(host pinned shard) + vi_build(fast, sharded) + vi_ranges_copy"},
-                  "replicate_ms": float(trep.item()), "search": search, "cpu_baseline": None}
+                  "replicate_ms": float(trep.item()), "search": search, "exact_mode": exact, "cpu_baseline": None}
         log(f"[{world} GPUs] build {ms_per_step:.2f} ms/step, e2e {e2e:.1f} ms/step; rank0 levels: "
             + str([(l.level, l.ranges, l.points, round(l.stats_ms, 2), round(l.partition_ms, 2)) for l in levels]))
         emit(result)
