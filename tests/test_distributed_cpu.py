@@ -212,3 +212,59 @@ def test_sharded_protocol_equals_single_rank_oracle(n, d, seed):
     L = 2
     deep = [set(k for k in res[r] if math.floor(math.log2(k + 1)) > L) for r in range(world)]
     assert all(len(s) > 0 for s in deep) and not (deep[0] & deep[1])
+
+
+# ---- exact-mode multi-rank protocol (vi_build.cu build_sharded_exact), restated over the literal oracle -------------------
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("n,d,seed", [(4000, 6, 21), (300, 3, 22)])
+def test_exact_mode_protocol_equals_single_rank_oracle(world, n, d, seed):
+    """Every rank holds all points, replays levels 0 .. L-1 (L = ceil(log2 world)) of the literal build, owns some of
+    the level-L ranges (largest first to the least loaded rank) and builds their sub-trees from the range's points in
+    stable order; the common rows plus the owned sub-trees must be the single-rank table, rank by rank disjoint."""
+    import oracle
+    rng = np.random.default_rng(seed)
+    rows = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    ids = (rng.permutation(n).astype(np.int64) * 3) + 1
+    ref = oracle.build(ids, rows, oracle.MODE_LITERAL)
+    want = {int(r): (int(dm), int(np.float32(m).view(np.uint32)), int(i))
+            for r, dm, m, i in zip(ref.range_id, ref.dimension, ref.mid, ref.id)}
+    L = 1
+    while (1 << L) < world:
+        L += 1
+    # the common top: partitions replayed from the rows of levels < L (what every rank computes for itself)
+    ranges = {0: np.arange(n)}
+    common = {}
+    for level in range(L):
+        nxt = {}
+        for rid, idx in ranges.items():
+            dim, midbits, pivot = want[rid]
+            common[rid] = want[rid]
+            if dim == -1:
+                continue
+            mid = np.array([midbits], np.uint32).view(np.float32)[0]
+            v = rows[idx, dim]
+            hi = (v > mid) | ((v == mid) & (ids[idx] > pivot))
+            for side, m in ((1, ~hi), (2, hi)):
+                if m.any():
+                    nxt[2 * rid + side] = idx[m]           # stable: index order is kept
+        ranges = nxt
+    open_ranges = sorted(ranges)                            # position order = RangeID order inside a level
+    sizes = [len(ranges[r]) for r in open_ranges]
+    order = sorted(range(len(open_ranges)), key=lambda i: -sizes[i])
+    load = [0] * world
+    owner = {}
+    for i in order:
+        best = min(range(world), key=lambda g: (load[g], g))
+        owner[open_ranges[i]] = best
+        load[best] += sizes[i]
+    union = dict(common)
+    for rank in range(world):
+        for rid in open_ranges:
+            if owner[rid] != rank:
+                continue
+            idx = ranges[rid]
+            sub = oracle.build(ids[idx], rows[idx], oracle.MODE_LITERAL, root_rid=rid, root_depth=L)
+            for r, dm, m, i in zip(sub.range_id, sub.dimension, sub.mid, sub.id):
+                assert int(r) not in union                  # no row is made twice
+                union[int(r)] = (int(dm), int(np.float32(m).view(np.uint32)), int(i))
+    assert union == want
