@@ -125,3 +125,34 @@ def test_hdf5_ingest_builds_the_same_index(tmp_path):
         b.reserve(10, 95)
         with pytest.raises(ValueError, match="Invalid length of vector"):
             b.add_hdf5(path, "/train")
+
+
+def test_corrupted_files_are_refused_or_read_never_crash(tmp_path):
+    # random byte corruptions and truncations of both container generations: the parser must answer with an error or
+    # with a data set that lies inside the file -- every read it then does is bounds-checked against the file size
+    rng = np.random.default_rng(1)
+    train = rng.standard_normal((200, 8), dtype=np.float32)
+    a, b = str(tmp_path / "a.h5"), str(tmp_path / "b.h5")
+    write_v0(a, {"train": train, "test": train[:5], "g": {"x": train[:3]}})
+    write_v2(b, {"train": train, "test": train[:5]})
+    answered = refused = 0
+    for base in (a, b):
+        raw = open(base, "rb").read()
+        for trial in range(250):
+            buf = bytearray(raw)
+            for _ in range(int(rng.integers(1, 4))):
+                buf[int(rng.integers(0, len(buf)))] = int(rng.integers(0, 256))
+            if trial % 10 == 0:
+                buf = buf[: int(rng.integers(8, len(buf)))]
+            q = tmp_path / "c.h5"
+            q.write_bytes(bytes(buf))
+            for name in ("/train", "/test", "/g/x"):
+                try:
+                    rows, cols, dt, off = vi.hdf5_dataset_info(str(q), name)
+                    assert rows >= 0 and cols >= 0 and off + rows * cols * dt.itemsize <= len(buf)
+                    if rows * cols * dt.itemsize < (1 << 24):
+                        vi.hdf5_read(str(q), name)
+                    answered += 1
+                except ValueError:
+                    refused += 1
+    assert answered > 0 and refused > 0
