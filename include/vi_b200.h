@@ -135,7 +135,7 @@ int64_t vi_points_count(const vi_ctx* ctx);
 int vi_build(vi_ctx* ctx, int32_t mode, vi_build_info* info);
 /* vi_build followed by vi_ranges_copy, as IndexBuilder.Build's consumer sees them (rows only after the build), with the
  * device-to-host copy of the table overlapped with the build's last kernel: that kernel finishes the sub-trees of <= 32
- * points in four slices whose row blocks are dense and contiguous, and each finished block is copied out (a second
+ * points in up to eight slices whose row blocks are dense and contiguous, and each finished block is copied out (a second
  * stream) while the next slice runs.  Host buffers should be pinned for the overlap to be real; any of them may be NULL.
  * *rows = rows of the table; VI_ERR_CAPACITY if cap is smaller (the build itself is complete and vi_ranges_copy works). */
 int vi_build_copy(vi_ctx* ctx, int32_t mode, vi_build_info* info, int64_t* range_id, int32_t* dimension, float* mid,

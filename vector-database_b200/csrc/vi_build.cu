@@ -550,9 +550,11 @@ static int run_subtrees(vi_ctx* ctx, BuildEnv& env, LevelState& s, const float* 
   const size_t smem = (size_t)SUB_WARPS * sub_smem_bytes_per_warp(rows_max, ld);
   // vi_build_copy: the list is taken in a few slices, and the dense row block of a finished slice (closed-form row
   // numbers: sub-tree k starts at row_base + 2 * sub_start[k] - 2 * k) goes to the host while the next slice runs
-  const int nslice = (ctx->out.active && s.sub_cnt >= 8192u) ? 4 : 1;
-  u32 kb[5] = {0, 0, 0, 0, s.sub_cnt};
-  u32 sb[5] = {0, 0, 0, 0, s.sub_pos};
+  const int nslice = (ctx->out.active && s.sub_cnt >= 8192u) ? (int)env_u32("VI_B200_COPY_SLICES", 8, 1, 8) : 1;
+  u32 kb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  u32 sb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  kb[nslice] = s.sub_cnt;
+  sb[nslice] = s.sub_pos;
   for (int i = 1; i < nslice; ++i)
   {
     kb[i] = (u32)((u64)s.sub_cnt * i / nslice);
