@@ -9,7 +9,10 @@
  * hold no golden vector / known-answer test for IndexBuilder.Build or dbo.Search.
  * The oracle is therefore anchored on the reference's *source text*, cited line by line below, plus
  * hand-derivable known answers kept in tests/test_oracle_kat.py and an independent numpy restatement in
- * oracle/np_oracle.py.
+ * oracle/np_oracle.py.  The one executable expectation the reference's tests do state -- Find + the Euclidean predicate
+ * returns exactly the plain scan's records on five fixed fixtures (MemoryVectorIndexTests.cs:10-113,161-204) -- is
+ * replayed against this oracle (build + search + verify) in tests/test_reference_fixtures.py: it pins the
+ * search-then-verify contract, not the rows of the range table.
  *
  * Reference files followed (paths relative to /root/reference):
  *   VectorIndex/IndexBuilder.cs:23-157   Build driver loop (DFS over ranges, explicit stack)
