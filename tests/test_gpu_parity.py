@@ -300,6 +300,31 @@ def test_cpp_host_mirror_main_test(mode):
     assert got == want
 
 
+def test_cpp_host_mirror_hdf5_path(tmp_path):
+    # cpp/main_test.cpp <mode> hdf5 <file>: Program.cs:86-150 -- `/train` of an HDF5 file through the native reader
+    import os
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from h5_writer import write_v0
+    ids, rows = ds.unit_gaussian(5000, 32, seed=31)
+    path = str(tmp_path / "train.hdf5")
+    write_v0(path, {"train": rows, "test": rows[:4]})
+    exe = os.path.join(os.path.dirname(vi.LIB_PATH), "main_test")
+    for mode, omode in ((vi.MODE_FAST, oracle.MODE_QFX), (vi.MODE_SQL, oracle.MODE_SQL)):
+        out = subprocess.run([exe, str(mode), "hdf5", path], check=True, capture_output=True, text=True).stdout
+        got = {}
+        for line in out.strip().splitlines():
+            r, d, bits, i = line.split(",")
+            got[int(r)] = (int(d), int(bits), int(i))
+        ref = oracle.build(np.arange(5000, dtype=np.int64), rows, omode)   # ids = row indexes, Program.cs:252
+        want = {int(r): (int(d), int(np.float32(m).view(np.uint32)), int(i))
+                for r, d, m, i in zip(ref.range_id, ref.dimension, ref.mid, ref.id)}
+        assert got == want
+    bad = subprocess.run([exe, "1", "hdf5", path, "/nope"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "no object named" in bad.stderr
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_nan_rows_overflow_like_the_reference(mode):
     # NaN components never compare greater than Mid, such points go low forever and the reference

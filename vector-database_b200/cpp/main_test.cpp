@@ -10,9 +10,33 @@
 
 using namespace NesterovskyBros::VectorIndex;
 
+static void print_rows(const std::vector<std::pair<int64_t, RangeValue>>& index)
+{
+  for (auto& [rangeId, range] : index)
+  {
+    uint32_t bits;
+    memcpy(&bits, &range.Mid, 4);
+    printf("%lld,%d,%u,%lld\n", (long long)rangeId, range.Dimension, bits, (long long)range.Id);
+  }
+}
+
 int main(int argc, char** argv)
 {
   const int mode = argc > 1 ? atoi(argv[1]) : 0;
+  if (argc > 3 && strcmp(argv[2], "hdf5") == 0)
+  {
+    // main_test <mode> hdf5 <file> [dataset]: the deep-image path of Program.cs:86-150
+    try
+    {
+      print_rows(IndexBuilder::BuildFromHdf5(argv[3], argc > 4 ? argv[4] : "/train", mode));
+    }
+    catch (const std::exception& e)
+    {
+      fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+    return 0;
+  }
   const int dimensions = argc > 2 ? atoi(argv[2]) : 1536;
   std::vector<Point> input;  // Program.cs:54-66
   for (int64_t i = 0; i < dimensions; ++i)
@@ -24,12 +48,7 @@ int main(int argc, char** argv)
   try
   {
     auto index = IndexBuilder::Build(input, [](int64_t, int64_t) { return std::make_unique<MemoryRangeStore>(); }, mode);
-    for (auto& [rangeId, range] : index)
-    {
-      uint32_t bits;
-      memcpy(&bits, &range.Mid, 4);
-      printf("%lld,%d,%u,%lld\n", (long long)rangeId, range.Dimension, bits, (long long)range.Id);
-    }
+    print_rows(index);
     // the rows alone are a searchable index (vi_ranges_load): a point lookup at proximity 0 must return the point
     RangeIndex lookup(index, dimensions);
     for (int64_t i = 0; i < dimensions && i < 16; ++i)

@@ -5,6 +5,7 @@
 //   RangeValue {Dimension, Mid, Id}            VectorIndex/RangeValue.cs:6-22
 //   VectorIndex::Find(vector, distance, pred)  shape of MemoryVectorIndex.cs:242-245 over dbo.Search (DDL.sql:234-295)
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <functional>
 #include <memory>
@@ -18,7 +19,7 @@ namespace NesterovskyBros::VectorIndex
 {
 struct RangeValue
 {
-  int32_t Dimension = 0;  // -1 = leaf
+  int32_t Dimension = 0;  // -1 = leaf; VI_DIM_NULL (-3) = null (VI_MODE_SQL, DDL.sql:193)
   float Mid = 0.0f;
   int64_t Id = 0;
 };
@@ -101,13 +102,35 @@ class IndexBuilder
       }
       Check(ctx.get(), vi_points_add(ctx.get(), ids.data(), rows.data(), (int64_t)(e - s), dims));
     }
-    Check(ctx.get(), vi_build(ctx.get(), mode, nullptr));
-    const int64_t k = vi_range_count(ctx.get());
-    std::vector<int64_t> rid(k), oid(k);
-    std::vector<int32_t> dim(k);
-    std::vector<float> mid(k);
-    Check(ctx.get(), vi_ranges_copy(ctx.get(), rid.data(), dim.data(), mid.data(), oid.data(), k));
-    out.reserve(k);
+    return Rows(ctx.get(), (int64_t)points.size(), mode);
+  }
+
+  // The real-data path of VectorIndex.MainTest (Program.cs:86-150): `/train` of an ANN-benchmarks HDF5 file, ids = row
+  // indexes (Program.cs:252), streamed to the device by the library's native reader.
+  static std::vector<std::pair<int64_t, RangeValue>> BuildFromHdf5(const char* fileName, const char* datasetName = "/train",
+                                                                   int mode = VI_MODE_EXACT, int device = 0)
+  {
+    CtxPtr ctx = MakeContext(device);
+    int64_t rows = 0, cols = 0;
+    Check(ctx.get(), vi_hdf5_dataset_info(ctx.get(), fileName, datasetName, &rows, &cols, nullptr, nullptr, nullptr));
+    if (rows == 0) return {};
+    Check(ctx.get(), vi_points_reserve(ctx.get(), rows, (int32_t)cols));
+    Check(ctx.get(), vi_points_add_hdf5(ctx.get(), fileName, datasetName, 0, -1, 0, nullptr, nullptr));
+    return Rows(ctx.get(), rows, mode);
+  }
+
+ private:
+  // vi_build_copy: build, then the rows -- the copy of the table's bulk overlaps the build's last kernel
+  static std::vector<std::pair<int64_t, RangeValue>> Rows(vi_ctx* ctx, int64_t n, int mode)
+  {
+    const int64_t cap = 2 * n + n / 8 + 1024;  // 2n - 1 rows, plus one per one-sided split
+    std::vector<int64_t> rid((size_t)cap), oid((size_t)cap);
+    std::vector<int32_t> dim((size_t)cap);
+    std::vector<float> mid((size_t)cap);
+    int64_t k = 0;
+    Check(ctx, vi_build_copy(ctx, mode, nullptr, rid.data(), dim.data(), mid.data(), oid.data(), cap, &k));
+    std::vector<std::pair<int64_t, RangeValue>> out;
+    out.reserve((size_t)k);
     for (int64_t i = 0; i < k; ++i) out.push_back({rid[i], RangeValue{dim[i], mid[i], oid[i]}});
     return out;
   }
@@ -139,10 +162,10 @@ class RangeIndex
   {
     if ((int32_t)vector.size() != dims_) throw std::invalid_argument("Invalid vector size.");  // MemoryVectorIndex.cs:254
     int64_t offsets[2] = {0, 0}, total = 0;
-    Check(ctx_.get(), vi_search(ctx_.get(), vector.data(), 1, dims_, proximity, offsets, nullptr, 0, &total));
-    std::vector<int64_t> ids((size_t)total);
-    if (total > 0)
-      Check(ctx_.get(), vi_search(ctx_.get(), vector.data(), 1, dims_, proximity, offsets, ids.data(), total, &total));
+    Check(ctx_.get(), vi_search_begin(ctx_.get(), vector.data(), 1, dims_, proximity, &total));  // one walk: count ...
+    std::vector<int64_t> ids((size_t)std::max<int64_t>(total, 1));
+    Check(ctx_.get(), vi_search_fetch(ctx_.get(), offsets, ids.data(), (int64_t)ids.size()));    // ... then fetch
+    ids.resize((size_t)total);
     return ids;
   }
 
