@@ -576,8 +576,8 @@ def main():
                 # `ncu --set full` (profiles/r1_ncu_final.md): 3.9606 GB + 4.4 MB for 3.96 GB of algorithmic bytes
                 "traffic": 3.965e9 if (n == 10_000_000 and DIMS == 96) else None,
                 "traffic_note": "level-0 launch (A = 10M points, nothing derived); algorithmic bytes of that launch 3.96e9; "
-                                "a level-2 launch with sibling derivation (4.27M rows summed): 1.696e9 for 1.689e9 "
-                                "(profiles/r1_ncu_final.md)",
+                                "a level-2 launch with sibling derivation (4.27M rows summed): 1.694e9 for 1.689e9 "
+                                "(ncu --set full, profiles/r2_ncu_chunk.md; the same figures as profiles/r1_ncu_final.md)",
                 "algorithmic_bytes_per_launch": stats_b / max(n_stats_launch, 1),
                 "avg_launch_ms": stats_ms / max(n_stats_launch, 1),
                 # SURVEY.md 8(d) as written (the level-by-level algorithm, every row read at every level): 412 B per point
